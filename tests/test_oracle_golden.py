@@ -1,0 +1,311 @@
+"""Pins the CPU oracle against every known-answer test the reference holds for the hot path.
+
+Each test names the reference spec it ports (/root/reference/test/LibSpec.hs unless noted).
+CPU only (-m "not gpu").
+"""
+import numpy as np
+import pytest
+
+import fixtures as F
+
+
+@pytest.fixture(scope="module")
+def o(ora):
+    return ora
+
+
+def _dense(o, fx):
+    return o.SpMatrix.fromListDenseSM(fx[0], fx[1])
+
+
+def _vr(o, ll):
+    return o.SpVector.mkSpVR(len(ll), ll)
+
+
+# ---- LibSpec.hs:45-46  "<.> : inner product (Real)"
+def test_dot_real(o):
+    tv0 = _vr(o, F.TV0)
+    assert tv0.dot(tv0) == 61
+
+
+# ---- LibSpec.hs:43-44 "Subtraction is cancellative"
+def test_sub_cancellative(o):
+    x = o.SpVector.fromListSV(7, [(1, 2.5), (4, -1.0), (6, 1e300)])
+    assert (x - x).norm2Sq() == 0
+
+
+# ---- LibSpec.hs:49-50 "transpose : sparse matrix transpose" (exact ==)
+def test_transpose_exact(o):
+    assert _dense(o, F.M1).transpose() == _dense(o, F.M1T)
+
+
+# ---- LibSpec.hs:51-54 "(#>)", "(<#)" (Real)
+def test_matvec_vecmat_real(o):
+    aa0, x0true, b0 = _dense(o, F.AA0), _vr(o, F.X0TRUE), _vr(o, F.B0)
+    assert o.nearZero((aa0.matVec(x0true) - b0).norm2Sq())
+    assert o.nearZero((aa0.vecMat(x0true) - _vr(o, F.AA0TX0)).norm2Sq())
+    # the products are small integers: exact
+    assert aa0.matVec(x0true).toDenseListSV().tolist() == [8.0, 18.0]
+    assert aa0.vecMat(x0true).toDenseListSV().tolist() == [11.0, 16.0]
+
+
+# ---- LibSpec.hs:61-65 "(##) : matrix-matrix product" (exact ==, incl. duplicate-overwrite)
+def test_matmat_exact(o):
+    assert _dense(o, F.M1).matMat(_dense(o, F.M2)) == _dense(o, F.M1M2)
+    m1p = o.SpMatrix.fromListSM(*F.M1P)
+    m2p = o.SpMatrix.fromListSM(*F.M2P)
+    assert m1p.matMat(m2p) == _dense(o, F.M1M2P)
+    # m2' ## m1' : the reference compares against a matrix WITHOUT explicit zeros (LibSpec.hs:1271)
+    # with derived Eq, so the product must store exactly those keys... it does not: (##) stores
+    # every (row, col) pair.  The reference spec passes because m2' has no stored row 1 and m1'
+    # has no stored column 1, so only the listed pairs exist.
+    assert m2p.matMat(m1p) == o.SpMatrix.fromListSM(*F.M2M1P)
+
+
+def test_fromlist_last_write_wins(o):
+    m = o.SpMatrix.fromListSM((2, 3), [(1, 2, 4.0), (1, 2, 1.0)])
+    assert m.toCOO()[2].tolist() == [1.0]
+    with pytest.raises(o.OracleError):          # insertSpMatrix : index out of bounds  SpMatrix.hs:205-208
+        o.SpMatrix.fromListSM((2, 2), [(0, 2, 1.0)])
+    # SpVector fromListSV: foldr => FIRST occurrence wins, out-of-bounds dropped  SpVector.hs:275-278
+    v = o.SpVector.fromListSV(3, [(1, 7.0), (1, 9.0), (5, 1.0)])
+    assert v.toListSV() == [(1, 7.0)]
+
+
+# ---- LibSpec.hs:68-69 "eye : identity matrix"  (nnz 10, density 0.1)
+def test_eye(o):
+    e = o.SpMatrix.eye(10)
+    assert e.nnz == 10 and e.nnz / (10 * 10) == 0.1
+    assert e.isDiagonalSM()
+
+
+# ---- LibSpec.hs:87-94 properties (prop_spd, prop_dot, prop_matMat1, prop_matMat2) on seeded random inputs
+def _rand_sm(o, rng, m, n):
+    k = int(np.sqrt(m * n)) + 1              # genSpM0: sqrt(mn) random triples, duplicates allowed (:720-730)
+    i = rng.integers(0, m, k)
+    j = rng.integers(0, n, k)
+    v = rng.standard_normal(k)
+    return o.SpMatrix.fromCOO((m, n), i, j, v)
+
+
+def _rand_sv(o, rng, n):
+    k = int(np.sqrt(n)) + 1                  # genSpV (:773-780)
+    idx = rng.integers(0, n, k)
+    return o.SpVector.fromListSV(n, list(zip(idx.tolist(), rng.standard_normal(k).tolist())))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_properties(o, seed):
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(2, 40)), int(rng.integers(2, 40))
+    mm = _rand_sm(o, rng, m, n)
+    v = _rand_sv(o, rng, n)
+    # prop_spd: v . (M^T M v) >= 0   (:944-946)
+    mtm = mm.transpose().matMat(mm)
+    assert v.dot(mtm.matVec(v)) >= 0
+    # prop_dot: normalized vector has unit self-dot  (:940-941)
+    if v.norm2() > 0:
+        vn = v.normalize2()
+        assert o.nearZero(1 - vn.dot(vn))
+    # prop_matMat1: (A ## B)^T == B^T ## A^T  exact   (:954-956)
+    b = _rand_sm(o, rng, n, int(rng.integers(2, 30)))
+    assert mm.matMat(b).transpose() == b.transpose().matMat(mm.transpose())
+
+
+# ---- LibSpec.hs:252-257 / 265-269 "cgsInit / bicgsInit creates initial state" (exact)
+def test_krylov_init_exact(o):
+    aa0, b0, x0 = _dense(o, F.AA0), _vr(o, F.B0), _vr(o, F.X0)
+    r0 = b0 - aa0.matVec(x0)
+    st = o.bicgsInit(aa0, b0, x0)
+    assert st.r == r0 and st.p == r0
+    st = o.cgsInit(aa0, b0, x0)
+    assert st.r == r0 and st.p == r0 and st.u == r0
+
+
+# ---- LibSpec.hs:258-263 / 270-275 "step performs one iteration"
+def test_krylov_step_keeps_dim(o):
+    aa0, b0, x0 = _dense(o, F.AA0), _vr(o, F.B0), _vr(o, F.X0)
+    rhat = b0 - aa0.matVec(x0)
+    assert o.bicgstabStep(aa0, rhat, o.bicgsInit(aa0, b0, x0)).x.dim == b0.dim
+    assert o.cgsStep(aa0, rhat, o.cgsInit(aa0, b0, x0)).x.dim == b0.dim
+
+
+def _check_solver(o, init, step, aa, b, niter):
+    """checkCGS / checkBiCGSTAB (LibSpec.hs:548-575, 606-632): x0 = empty vector, true-residual exit."""
+    x0 = o.SpVector.fromListSV(b.dim, [])
+    rhat = b - aa.matVec(x0)
+    st = init(aa, b, x0)
+    tol = max(1e-6, 1e-4 * st.r.norm2())
+    res = lambda s: (aa.matVec(s.x) - b).norm2()
+    n = 0
+    while n < niter:
+        st = step(aa, rhat, st)
+        n += 1
+        if res(st) <= tol:
+            break
+    return res(st) <= tol, n, st
+
+
+# ---- LibSpec.hs:259-262, 276-279: converge on aa0 (2x2) and aa2 (3x3 SPD) within 50 iterations
+@pytest.mark.parametrize("solver", ["cgs", "bicgstab"])
+@pytest.mark.parametrize("system", ["aa0", "aa2"])
+def test_solver_converges(o, solver, system):
+    aa = _dense(o, F.AA0) if system == "aa0" else _dense(o, F.AA2).sparsifySM()
+    b = _vr(o, F.B0 if system == "aa0" else F.B2)
+    init, step = (o.cgsInit, o.cgsStep) if solver == "cgs" else (o.bicgsInit, o.bicgstabStep)
+    ok, n, _ = _check_solver(o, init, step, aa, b, 50)
+    assert ok and n <= 50
+
+
+# ---- LibSpec.hs:264-284 prop_cgs / prop_bicgstab on M^T M + 2I (generator :914-922, guards :990-1009)
+@pytest.mark.parametrize("seed", range(8))
+def test_prop_solvers_spd(o, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(3, 20))
+    m = _rand_sm(o, rng, n, n)
+    mtm = m.transpose().matMat(m)
+    i, j, v = mtm.toCOO()
+    ii = np.concatenate([i, np.arange(n)])
+    jj = np.concatenate([j, np.arange(n)])
+    d = mtm.toDense() + 2.0 * np.eye(n)
+    spd = o.SpMatrix.fromCOO((n, n), ii, jj, d[ii, jj])
+    x = o.SpVector.mkSpVR(n, rng.standard_normal(n))
+    b = spd.matVec(x)
+    if b.norm2() < 1e-10 or x.norm2() < 1e-10 or spd.nnz < n:
+        return
+    for init, step in ((o.cgsInit, o.cgsStep), (o.bicgsInit, o.bicgstabStep)):
+        ok, _, _ = _check_solver(o, init, step, spd, b, 100)
+        assert ok
+
+
+# ---- LibSpec.hs:286-300 linSolve0 x {BICGSTAB_, CGS_, CGNE_} x {aa0, aa2}, x0 = 0.1, ||x - xhat|| <= 1e-12
+@pytest.mark.parametrize("method", ["BICGSTAB_", "CGS_", "CGNE_"])
+@pytest.mark.parametrize("system", ["aa0", "aa2"])
+def test_linsolve0(o, method, system):
+    aa = _dense(o, F.AA0) if system == "aa0" else _dense(o, F.AA2).sparsifySM()
+    b = _vr(o, F.B0 if system == "aa0" else F.B2)
+    xt = _vr(o, F.X0TRUE if system == "aa0" else F.X2)
+    n = aa.ncols
+    x0r = o.SpVector.mkSpVR(n, [0.1] * n)
+    xhat = o.linSolve0(getattr(o, method), aa, b, x0r)
+    assert o.nearZero((xt - xhat).norm2())
+
+
+def test_linsolve0_errors_and_diagonal(o):
+    aa0, b0 = _dense(o, F.AA0), _vr(o, F.B0)
+    x0r = o.SpVector.mkSpVR(2, [0.1, 0.1])
+    with pytest.raises(o.OracleError) as e:    # IterE "linSolve0" ... Sparse.hs:1031
+        o.linSolve0(o.GMRES_, aa0, b0, x0r)
+    assert e.value.code == o.ORA_ERR_UNSUPPORTED_METHOD
+    with pytest.raises(o.OracleError) as e:    # MatVecSizeMismatchException Sparse.hs:1022
+        o.linSolve0(o.BICGSTAB_, aa0, o.SpVector.mkSpVR(3, [1, 2, 3]), x0r)
+    assert e.value.code == o.ORA_ERR_SIZE_MISMATCH
+    d = o.SpMatrix.fromListSM((3, 3), [(0, 0, 2.0), (1, 1, 4.0), (2, 2, 8.0)])   # diagonal shortcut :1024-1025
+    x = o.linSolve0(o.BCG_, d, o.SpVector.mkSpVR(3, [2, 2, 2]), o.SpVector.zeroSV(3))
+    assert x.toDenseListSV().tolist() == [1.0, 0.5, 0.25]
+
+
+# ---- README.md:97, 183-241 worked example: amat x = b, x = [1.5, -2, 1]
+def test_readme_example(o):
+    amat = o.SpMatrix.fromListSM(*F.AMAT)
+    b = _vr(o, F.AMAT_B)
+    x0 = o.SpVector.fromListSV(3, [])
+    rhat = b - amat.matVec(x0)
+    st = o.bicgsInit(amat, b, x0)
+    for _ in range(3):
+        st = o.bicgstabStep(amat, rhat, st)
+    np.testing.assert_allclose(st.x.toDenseListSV(), F.AMAT_X, atol=1e-9)
+    x = o.linSolve0(o.BICGSTAB_, amat, b, x0)
+    np.testing.assert_allclose(x.toDenseListSV(), F.AMAT_X, atol=1e-5)
+
+
+# ---- LibSpec.hs:226-232 Arnoldi: || A Q' - Q H ||_F nearZero, b = ones  (checkArnoldi :638-653)
+@pytest.mark.parametrize("which,kn", [("aa4", 3), ("tm7", 4)])
+def test_arnoldi(o, which, kn):
+    aa = _dense(o, F.AA4) if which == "aa4" else o.SpMatrix.fromListSM(*F.tm7_triples())
+    b = o.SpVector.onesSV(aa.nrows)
+    Q, H = o.arnoldi(aa, b, kn)
+    m, n = Q.shape
+    assert H.shape[0] == H.shape[1] + 1 and n == H.shape[0]
+    A = aa.toDense()
+    diff = A @ Q[:, : n - 1] - Q @ H
+    assert np.linalg.norm(diff) <= 1e-12
+    # Q has orthonormal columns unless breakdown occurred
+    if not o.nearZero(H[-1, -1]):
+        np.testing.assert_allclose(Q.T @ Q, np.eye(n), atol=1e-9)
+
+
+# ---- SURVEY.md §8(c) derived trajectories (hand-emulated sequential order; regression values, tol 1e-12)
+def test_derived_trajectories(o):
+    aa0, b0 = _dense(o, F.AA0), _vr(o, F.B0)
+    x, iters, hist = o.linSolve0(o.BICGSTAB_, aa0, b0, o.SpVector.mkSpVR(2, [0.1, 0.1]), info=True)
+    assert iters == 2
+    np.testing.assert_allclose(hist[0], 1.9650020182149508e-1, rtol=1e-10)
+    np.testing.assert_allclose(x.toDenseListSV(), [1.9999999999996778, 3.0000000000002385], atol=1e-12)
+    # first iterate
+    x0 = o.SpVector.mkSpVR(2, [0.1, 0.1])
+    rhat = b0 - aa0.matVec(x0)
+    st = o.bicgstabStep(aa0, rhat, o.bicgsInit(aa0, b0, x0))
+    np.testing.assert_allclose(st.x.toDenseListSV(), [1.5909602733108075, 3.302374038323529], atol=1e-12)
+    # checkBiCGSTAB aa0 b0 (x0 empty): 2 iterations
+    ok, n, st = _check_solver(o, o.bicgsInit, o.bicgstabStep, aa0, b0, 50)
+    assert ok and n == 2
+    np.testing.assert_allclose(st.x.toDenseListSV(), [1.999999999999913, 3.0000000000000644], atol=1e-12)
+    # aa2, x0 = 0.1
+    aa2, b2 = _dense(o, F.AA2).sparsifySM(), _vr(o, F.B2)
+    x0 = o.SpVector.mkSpVR(3, [0.1] * 3)
+    rhat = b2 - aa2.matVec(x0)
+    st = o.bicgstabStep(aa2, rhat, o.bicgsInit(aa2, b2, x0))
+    np.testing.assert_allclose(st.x.toDenseListSV(),
+                               [1.6851254896964363, 0.360675935205946, 1.6851254896964363], atol=1e-12)
+    x, iters, _ = o.linSolve0(o.BICGSTAB_, aa2, b2, x0, info=True)
+    assert iters == 2
+    np.testing.assert_allclose(x.toDenseListSV(), [3, 2, 3], atol=1e-13)
+
+
+# ---- independent cross-check of the restatement against scipy on random inputs
+@pytest.mark.parametrize("seed", range(4))
+def test_matvec_vs_scipy(o, seed):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(seed)
+    m, n, k = 60, 50, 400
+    i, j, v = rng.integers(0, m, k), rng.integers(0, n, k), rng.standard_normal(k)
+    aa = o.SpMatrix.fromCOO((m, n), i, j, v)
+    # scipy sums duplicates, the reference overwrites: dedupe (last wins) before comparing
+    last = {}
+    for q in range(k):
+        last[(int(i[q]), int(j[q]))] = v[q]
+    ii = np.array([a for a, _ in last]); jj = np.array([b for _, b in last]); vv = np.array(list(last.values()))
+    s = sp.csr_matrix((vv, (ii, jj)), shape=(m, n))
+    x = rng.standard_normal(n)
+    y = aa.matVec(o.SpVector.mkSpVR(n, x)).toDenseListSV()
+    np.testing.assert_allclose(y, s @ x, rtol=1e-13, atol=1e-13)
+    # CSR view: ascending columns, bit-exact values
+    rp, c, val = aa.toCSR()
+    s.sort_indices()
+    assert rp.tolist() == s.indptr.tolist() and c.tolist() == s.indices.tolist()
+    assert val.tolist() == s.data.tolist()
+    # transpose bit-exact vs scipy
+    t = s.T.tocsr(); t.sort_indices()
+    rp, c, val = aa.transpose().toCSR()
+    assert rp.tolist() == t.indptr.tolist() and c.tolist() == t.indices.tolist() and val.tolist() == t.data.tolist()
+
+
+def test_synth_rows(o):
+    # diag-dominant, sorted, distinct, exactly k entries; banded stays within the band
+    n, k = 1000, 32
+    for kind, band in ((o.GEN_UNIFORM, 0), (o.GEN_BANDED, 40)):
+        for i in (0, 1, 17, 500, 999):
+            cols, vals = o.synth_row(kind, n, k, 0x5EED0001, band, i)
+            assert len(cols) == k and np.all(np.diff(cols) > 0) and i in cols
+            if kind == o.GEN_BANDED:
+                assert cols.min() >= max(0, i - band) and cols.max() <= min(n - 1, i + band)
+            d = vals[cols == i][0]
+            assert d == pytest.approx(1 + np.abs(vals[cols != i]).sum(), rel=1e-14)
+    cols, vals = o.synth_row(o.GEN_LAPLACE2D, 16, 5, 0, 4, 5)
+    assert cols.tolist() == [1, 4, 5, 6, 9] and vals.tolist() == [-1, -1, 4, -1, -1]
+    cols, vals = o.synth_row(o.GEN_LAPLACE2D, 16, 5, 0, 4, 0)
+    assert cols.tolist() == [0, 1, 4]
+    a = o.SpMatrix.synth(o.GEN_LAPLACE2D, 16, 5, 0, 4)
+    assert a.nnz == 5 * 16 - 4 * 4
