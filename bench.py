@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200: fp64 CSR SpMV GB/s (% of the HBM roofline) and
+BiCGSTAB iterations/s, on the configurations BASELINE.json names.
+
+    python bench.py --gpus 1 --steps 200 --warmup 20            # this framework (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus 1 --steps 5 --warmup 3   # the reference's CPU algorithm (oracle port)
+
+A step = one (#>) over the synthetic 10M x 10M, 32 nnz/row matrix of SURVEY.md §8(d) config 2 (uniform
+columns).  `value` = algorithmic bytes (12 nnz + 20 n + 4) x steps / device time, inputs resident in HBM;
+`e2e` = the same metric through the host-buffer C-ABI call sla_spmv_host (pinned host x -> device, kernel,
+device y -> host inside the timed region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "csr_spmv_fp64_gbs"
+N_CFG2, K_CFG2, SEED_CFG2 = 10_000_000, 32, 0x5EED0002
+G_CFG3 = 4096
+FALLBACK_HBM_GBS = 6650.0
+
+
+def load_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+def load_traffic():
+    """DRAM bytes per SpMV launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("spmv_cfg2_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def spmv_bytes(n, nnz):
+    return 12 * nnz + 20 * n + 4
+
+
+def cpu_baseline(threads, n_sample=2_000_000, reps=3):
+    """The oracle's (#>) (per-row ordered intersection + left fold, the reference's algorithm) timed on the
+    host cores on a bounded sample of config 2: same family, n_sample rows x 32 nnz/row."""
+    from oracle import oracle as ora
+
+    ora.build()
+    A = ora.SpMatrix.synth(ora.GEN_UNIFORM, n_sample, K_CFG2, SEED_CFG2)
+    x = ora.SpVector.synth(SEED_CFG2 + 1, n_sample)
+    ora.time_matvec(A, x, 1, threads)
+    sec = ora.time_matvec(A, x, reps, threads)
+    gbs = spmv_bytes(n_sample, n_sample * K_CFG2) / sec / 1e9
+    return gbs, sec, f"config-2 family (uniform, 32 nnz/row) at n={n_sample} rows ({n_sample * K_CFG2} nnz), {reps} matvecs"
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm for the path (oracle port; the Haskell cannot be
+    built here: no GHC), all host threads, each step a bounded sample of config 2."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as ora
+
+    ora.build()
+    threads = os.cpu_count() or 1
+    n_sample = 2_000_000
+    A = ora.SpMatrix.synth(ora.GEN_UNIFORM, n_sample, K_CFG2, SEED_CFG2)
+    x = ora.SpVector.synth(SEED_CFG2 + 1, n_sample)
+    for _ in range(args.warmup):
+        ora.time_matvec(A, x, 1, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ora.time_matvec(A, x, 1, threads)
+    sec = (time.perf_counter() - t0) / args.steps
+    gbs = spmv_bytes(n_sample, n_sample * K_CFG2) / sec / 1e9
+    sample = f"config-2 family (uniform, 32 nnz/row) at n={n_sample} rows per step; GB/s is size-normalised"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: CSR SpMV (#>) fp64, 10M x 10M, 32 nnz/row, uniform columns (bounded sample)",
+                   "sample_rows": n_sample, "nnz_per_row": K_CFG2},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import sparse_linear_algebra_b200 as sla
+
+    ctx = sla.Context(local)
+    sla.set_default_context(ctx)
+
+    def barrier():
+        if dist is not None:
+            import torch
+
+            dist.barrier()
+            torch.cuda.synchronize()
+        ctx.sync()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- config 2: SpMV.  Weak scaling: every rank owns a 10M-row block (replicated family, own seed).
+    n, k = N_CFG2, K_CFG2
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, SEED_CFG2 + 7919 * rank)
+    x = sla.SpVector.generate(n, SEED_CFG2 + 1)
+    y = sla.SpVector.zeroSV(n)
+    nbytes = A.spmv_bytes
+    for _ in range(args.warmup):
+        A.matVec(x, out=y)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    ctx.timer_start()
+    for _ in range(args.steps):
+        A.matVec(x, out=y)
+    ms = ctx.timer_stop()
+    barrier()
+    launches = ctx.launches - l0
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = world * nbytes / (ms_per_step * 1e-3) / 1e9
+    kernel_gbs = nbytes / (ms_per_step * 1e-3) / 1e9          # one launch per step: the SpMV kernel itself
+
+    # ---- e2e: host buffers through sla_spmv_host (pinned x -> device, kernel, device y -> host)
+    xh = ctx.pinned(n)
+    yh = ctx.pinned(n)
+    xh[:] = x.toDenseListSV()
+    import ctypes as C
+
+    pd = C.POINTER(C.c_double)
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        ctx.check(ctx.lib.sla_spmv_host(ctx.h, A.h, xh.ctypes.data_as(pd), yh.ctypes.data_as(pd)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.check(ctx.lib.sla_spmv_host(ctx.h, A.h, xh.ctypes.data_as(pd), yh.ctypes.data_as(pd)))
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_gbs = world * nbytes / e2e_s / 1e9
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- banded variant of config 2 (columns within +-65536 of the row) for context
+    extra = {}
+    if world == 1 and not args.quick:
+        del A
+        B = sla.SpMatrix.generate(sla.GEN_BANDED, n, k, SEED_CFG2, 65536)
+        for _ in range(args.warmup):
+            B.matVec(x, out=y)
+        ctx.timer_start()
+        for _ in range(args.steps):
+            B.matVec(x, out=y)
+        msb = ctx.timer_stop() / args.steps
+        extra["spmv_banded_gbs"] = B.spmv_bytes / (msb * 1e-3) / 1e9
+        extra["spmv_banded_ms"] = msb
+        del B
+        # ---- config 3: BiCGSTAB on the 5-point Laplacian 4096^2, fixed number of bicgstabStep calls
+        g = G_CFG3
+        n3 = g * g
+        L3 = sla.SpMatrix.generate(sla.GEN_LAPLACE2D, n3, 5, 0, g)
+        xt = sla.SpVector.generate(n3, 3)
+        b = L3 @ xt
+        st = sla.bicgsInit(L3, b, sla.SpVector.zeroSV(n3))
+        rhat = st.r.copy()
+        its = max(10, min(args.steps, 100))
+        for _ in range(5):
+            sla.bicgstabStep(L3, rhat, st)
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(its):
+            sla.bicgstabStep(L3, rhat, st)
+        ms3 = ctx.timer_stop() / its
+        b3 = 24 * L3.nnz + 168 * n3                       # B_bicgstab_step, SURVEY.md §8(d)
+        extra["bicgstab_cfg3_iters_per_s"] = 1e3 / ms3
+        extra["bicgstab_cfg3_ms_per_iter"] = ms3
+        extra["bicgstab_cfg3_gbs"] = b3 / (ms3 * 1e-3) / 1e9
+        ctx.timer_start()
+        for _ in range(its):
+            L3.matVec(xt, out=b)
+        ms3s = ctx.timer_stop() / its
+        extra["spmv_cfg3_gbs"] = L3.spmv_bytes / (ms3s * 1e-3) / 1e9
+        del L3, st
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peak()
+    for key in ("spmv_banded_gbs", "bicgstab_cfg3_gbs", "spmv_cfg3_gbs"):
+        if key in extra:
+            extra[key.replace("_gbs", "_frac")] = extra[key] / peak
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        gbs, sec, sample = cpu_baseline(threads)
+        cpu = {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
+               "seconds_per_matvec_on_sample": sec}
+    out = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: CSR SpMV (#>) fp64, 10M x 10M, 32 nnz/row, uniform columns, 1 x B200 per rank",
+                   "n": n, "nnz": n * k, "algorithmic_bytes_per_step": nbytes,
+                   "l2": "no flush: the 3.84 GB matrix stream exceeds the 126 MB L2 every step"},
+        "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
+                     "traffic": load_traffic(), "peak_source": peak_src, "kernel": "spmv_tile_kernel<2048, EPI_NONE>"},
+        "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                "ms_per_step": e2e_s * 1e3, "api": "sla_spmv_host (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "cpu_baseline": cpu,
+        "extra": extra,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="skip the banded / BiCGSTAB context runs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

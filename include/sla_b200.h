@@ -1,0 +1,160 @@
+/* sla_b200.h — C ABI of libsla_b200.so, the B200 (sm_100a) sparse Krylov backend that drops in behind
+ * Numeric.LinearAlgebra.Sparse's operator surface (ocramz/sparse-linear-algebra, commit b940b12).
+ *
+ * The reference has no FFI; the boundary it exposes is the typeclass surface of
+ * src/Numeric/LinearAlgebra/Class.hs as instantiated for SpVector Double / SpMatrix Double.  Each
+ * entry point below names the reference function it replaces (paths under the reference root).
+ * A Haskell shim binds these with `foreign import ccall safe` (hs/).
+ *
+ * Conventions
+ *  - plain C: opaque handles, pointers and sizes; no C++ or torch types cross the boundary.
+ *  - host pointers are BORROWED for the duration of one call; device memory never crosses.
+ *  - every call returns sla_status; sla_last_error(ctx) gives the message (it mirrors the Show
+ *    instance of the reference exception, src/Control/Exception/Common.hs:44-76).
+ *  - one sla_ctx = one GPU = one host thread at a time (the reference is single-threaded and pure).
+ *    Multi-GPU is one process (one ctx) per GPU; ranks are joined with sla_init_dist.
+ *  - vectors are dense double[n] on the device: an absent SpVector key marshals as 0.0.
+ *  - matrices are CSR (int32 row_ptr[m+1], int32 col_idx[nnz] ascending per row, double val[nnz]);
+ *    field meaning follows vector/src/Data/Sparse/Internal/CSR.hs:38-50.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry returns SLA_ERR_CUDA.
+ */
+#ifndef SLA_B200_H
+#define SLA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sla_ctx sla_ctx;
+typedef struct sla_csr sla_csr;       /* SpMatrix Double   src/Data/Sparse/SpMatrix.hs:52-54 */
+typedef struct sla_vec sla_vec;       /* SpVector Double   src/Data/Sparse/SpVector.hs:42-43 */
+typedef struct sla_dense sla_dense;   /* dense column-major block (Krylov basis Q; `##` right operand) */
+typedef struct sla_krylov sla_krylov; /* BICGSTAB / CGS / CGNE records   src/Numeric/LinearAlgebra/Sparse.hs:855, 921, 962 */
+
+typedef enum {
+  SLA_OK = 0,
+  SLA_ERR_SIZE_MISMATCH = 1,      /* MatVecSizeMismatchException / error "matVec : mismatched dimensions"  Common.hs:250, Sparse.hs:637,1022 */
+  SLA_ERR_OOB_INDEX = 2,          /* error "insertSpMatrix : index out of bounds"  SpMatrix.hs:205-208 */
+  SLA_ERR_UNSUPPORTED_METHOD = 3, /* IterE "linSolve0" "Only BICGSTAB_, CGS_, and CGNE_ ..."  Sparse.hs:1031 */
+  SLA_ERR_NOT_CONVERGED = 4,      /* informational only: the reference returns x silently after nits  Sparse.hs:1045 */
+  SLA_ERR_BREAKDOWN = 5,          /* informational: Arnoldi breakdown, nearZero h_{i+1,i}  Sparse.hs:666 */
+  SLA_ERR_CUDA = 6,
+  SLA_ERR_COMM = 7,
+  SLA_ERR_ALLOC = 8,
+  SLA_ERR_INVALID = 9
+} sla_status;
+
+/* LinSolveMethod  Sparse.hs:1007-1012 (constructor order) */
+typedef enum { SLA_GMRES_ = 0, SLA_CGNE_ = 1, SLA_BCG_ = 2, SLA_CGS_ = 3, SLA_BICGSTAB_ = 4 } sla_method;
+
+/* fields of a Krylov record for sla_krylov_get: _x,_r,_p,_u  Sparse.hs:921, 962-963 */
+typedef enum { SLA_FIELD_X = 0, SLA_FIELD_R = 1, SLA_FIELD_P = 2, SLA_FIELD_U = 3 } sla_field;
+
+/* ---- context ------------------------------------------------------------------------------ */
+sla_status  sla_init(int device, sla_ctx** out);
+/* one rank of a row-partitioned multi-GPU job; nccl_id = 128 bytes from sla_nccl_unique_id on rank 0 */
+sla_status  sla_nccl_unique_id(void* out128);
+sla_status  sla_init_dist(int device, int rank, int world, const void* nccl_id128, sla_ctx** out);
+void        sla_finalize(sla_ctx*);
+const char* sla_last_error(const sla_ctx*);
+const char* sla_version(void);
+sla_status  sla_sync(sla_ctx*);
+void*       sla_stream(sla_ctx*);                  /* the cudaStream_t every kernel of this ctx is launched on */
+int         sla_rank(const sla_ctx*);
+int         sla_world(const sla_ctx*);
+int64_t     sla_launch_count(const sla_ctx*);      /* kernels launched by this ctx so far */
+/* page-locked host buffers for the host-pointer entry points (Haskell: wrap in a ForeignPtr with sla_host_free) */
+sla_status  sla_host_alloc(sla_ctx*, int64_t bytes, void** out);
+void        sla_host_free(void*);
+sla_status  sla_timer_start(sla_ctx*);             /* CUDA events on the ctx stream */
+sla_status  sla_timer_stop(sla_ctx*, float* ms);
+
+/* ---- matrices (construction is setup, not the timed path) ---------------------------------- */
+/* fromListSM (m,n) [(i,j,v)]: later duplicates overwrite, out-of-bounds is an error.  SpMatrix.hs:205-224 */
+sla_status sla_csr_from_coo(sla_ctx*, int64_t m, int64_t n, int64_t nnz, const int64_t* i, const int64_t* j,
+                            const double* v, sla_csr** out);
+/* already-CSR input (columns ascending and unique per row; validated) */
+sla_status sla_csr_from_csr(sla_ctx*, int64_t m, int64_t n, int64_t nnz, const int32_t* row_ptr,
+                            const int32_t* col_idx, const double* val, sla_csr** out);
+/* synthetic workloads of SURVEY.md §8(d), generated on the device from include/sla_synth.h */
+sla_status sla_csr_generate(sla_ctx*, int kind, int64_t n, int nnz_per_row, uint64_t seed, int64_t band,
+                            sla_csr** out);
+sla_status sla_csr_dims(const sla_csr*, int64_t* m, int64_t* n, int64_t* nnz);
+sla_status sla_csr_to_host(sla_ctx*, const sla_csr*, int32_t* row_ptr, int32_t* col_idx, double* val);
+sla_status sla_csr_transpose(sla_ctx*, const sla_csr*, sla_csr** out);         /* transposeSM  SpMatrix.hs:717-718 (bit-exact) */
+sla_status sla_csr_is_diagonal(sla_ctx*, const sla_csr*, int* out);            /* isDiagonalSM SpMatrix.hs:411-415 */
+int64_t    sla_csr_spmv_bytes(const sla_csr*);                                 /* algorithmic bytes of one (#>): 12 nnz + 20 n + 4 */
+void       sla_csr_free(sla_csr*);
+
+/* ---- vectors ------------------------------------------------------------------------------- */
+sla_status sla_vec_create(sla_ctx*, int64_t n, sla_vec** out);                           /* zeros */
+sla_status sla_vec_from_host(sla_ctx*, int64_t n, const double* x, sla_vec** out);       /* mkSpVR / fromListDenseSV  SpVector.hs:183-195 */
+sla_status sla_vec_generate(sla_ctx*, int64_t n, uint64_t seed, sla_vec** out);          /* sla_synth_vec */
+sla_status sla_vec_upload(sla_ctx*, sla_vec*, const double* x);                          /* overwrite from host */
+sla_status sla_vec_to_host(sla_ctx*, const sla_vec*, double* x);                         /* toDenseListSV  SpVector.hs:300-301 */
+sla_status sla_vec_copy(sla_ctx*, const sla_vec* src, sla_vec* dst);
+sla_status sla_vec_fill(sla_ctx*, sla_vec*, double a);                                   /* constv  SpVector.hs:232-233 */
+int64_t    sla_vec_dim(const sla_vec*);
+void       sla_vec_free(sla_vec*);
+
+/* ---- operator surface  (Class.hs:57-99, 126-153, 224-229) ---------------------------------- */
+sla_status sla_spmv (sla_ctx*, const sla_csr* A, const sla_vec* x, sla_vec* y);          /* (#>) = matVecSD  Common.hs:242-250 */
+sla_status sla_spmvT(sla_ctx*, const sla_csr* A, const sla_vec* x, sla_vec* y);          /* (<#) = vecMatSD  Common.hs:253-256 */
+sla_status sla_dot  (sla_ctx*, const sla_vec* x, const sla_vec* y, double* out);         /* (<.>)  SpVector.hs:116-117 */
+sla_status sla_norm2sq(sla_ctx*, const sla_vec* x, double* out);                         /* norm2Sq SpVector.hs:122 */
+sla_status sla_norm2(sla_ctx*, const sla_vec* x, double* out);                           /* norm2 / norm2'  SpVector.hs:127-128 */
+sla_status sla_vec_add  (sla_ctx*, const sla_vec* x, const sla_vec* y, sla_vec* z);      /* z = x ^+^ y   SpVector.hs:107-109 */
+sla_status sla_vec_sub  (sla_ctx*, const sla_vec* x, const sla_vec* y, sla_vec* z);      /* z = x ^-^ y   Class.hs:68-69 */
+sla_status sla_vec_scale(sla_ctx*, double a, const sla_vec* x, sla_vec* z);              /* z = a .* x    SpVector.hs:112-114 */
+sla_status sla_vec_axpy (sla_ctx*, double a, const sla_vec* x, const sla_vec* y, sla_vec* z); /* z = y ^+^ (a .* x), rounded as written */
+sla_status sla_vec_normalize2(sla_ctx*, const sla_vec* x, sla_vec* z);                   /* z = x ./ norm2 x  SpVector.hs:125, Class.hs:94-95 */
+/* host-buffer form of (#>): x and y live in host memory, copies are part of the call (bench e2e leg) */
+sla_status sla_spmv_host(sla_ctx*, const sla_csr* A, const double* x_host, double* y_host);
+
+/* ---- Krylov  (Sparse.hs:855-981) ----------------------------------------------------------- */
+sla_status sla_bicgstab_init(sla_ctx*, const sla_csr* A, const sla_vec* b, const sla_vec* x0, sla_krylov** st); /* bicgsInit :965-968 */
+sla_status sla_bicgstab_step(sla_ctx*, const sla_csr* A, const sla_vec* r0hat, sla_krylov* st);                 /* bicgstabStep :970-981 */
+sla_status sla_cgs_init(sla_ctx*, const sla_csr* A, const sla_vec* b, const sla_vec* x0, sla_krylov** st);      /* cgsInit :923-926 */
+sla_status sla_cgs_step(sla_ctx*, const sla_csr* A, const sla_vec* rhat, sla_krylov* st);                       /* cgsStep :928-939 */
+sla_status sla_cgne_init(sla_ctx*, const sla_csr* A, const sla_vec* b, const sla_vec* x0, sla_krylov** st);     /* cgneInit :862-866 */
+sla_status sla_cgne_step(sla_ctx*, const sla_csr* A, sla_krylov* st);                                           /* cgneStep :868-878 */
+sla_status sla_krylov_get(sla_ctx*, const sla_krylov*, int field, double* host_out);                            /* _x / _r / _p / _u */
+sla_status sla_krylov_view(sla_ctx*, const sla_krylov*, int field, const sla_vec** view);                       /* borrowed device view */
+void       sla_krylov_free(sla_krylov*);
+
+typedef struct {
+  int    max_iters;      /* nits   = 200   Sparse.hs:1034 */
+  double tol_abs;        /* tolAbs = 1e-6  Sparse.hs:1035 */
+  double tol_rel;        /* tolRel = 1e-4  Sparse.hs:1036 */
+  int    true_residual;  /* 1: ||A x - b|| recomputed (reference behaviour, Sparse.hs:1041); 0: recurrence residual ||r|| */
+  int    check_every;    /* 1: test every iteration (reference) */
+} sla_solve_opts;
+void sla_solve_opts_default(sla_solve_opts*);
+
+/* linSolve0 method aa b x0  (Sparse.hs:1016-1072).  x receives the solution; *iters the number of steps taken;
+ * *resnorm the last residual norm tested.  Reaching max_iters returns SLA_OK (the reference returns x silently). */
+sla_status sla_linsolve0(sla_ctx*, int method, const sla_csr* A, const sla_vec* b, const sla_vec* x0,
+                         const sla_solve_opts*, sla_vec* x, int* iters, double* resnorm);
+sla_status sla_linsolve0_host(sla_ctx*, int method, const sla_csr* A, const double* b_host, const double* x0_host,
+                              const sla_solve_opts*, double* x_host, int* iters, double* resnorm);
+
+/* arnoldi aa b kn  (Sparse.hs:630-667).  Q: n x (*nmax + 1) dense column-major on the device (sla_dense);
+ * H: (nmax+1) x nmax column-major, written to the host buffer h_host (capacity (kn+1)*kn doubles, kn >= 2).
+ * Returns SLA_ERR_BREAKDOWN (informational, outputs valid) if nearZero h_{i+1,i} stopped it early. */
+sla_status sla_arnoldi(sla_ctx*, const sla_csr* A, const sla_vec* b, int kn, sla_dense** Q, double* h_host, int* nmax);
+/* restarted GMRES(restart) built on the same Arnoldi kernels (the reference's gmres is commented out,
+ * Sparse.hs:837-848; `<\>` was meant to call it, Sparse.hs:1082-1088). */
+sla_status sla_gmres(sla_ctx*, const sla_csr* A, const sla_vec* b, const sla_vec* x0, int restart,
+                     const sla_solve_opts*, sla_vec* x, int* iters, double* resnorm);
+
+/* ---- dense blocks -------------------------------------------------------------------------- */
+sla_status sla_dense_dims(const sla_dense*, int64_t* rows, int64_t* cols);
+sla_status sla_dense_to_host(sla_ctx*, const sla_dense*, double* out_colmajor);
+void       sla_dense_free(sla_dense*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLA_B200_H */

@@ -1,0 +1,229 @@
+// common.cuh — internal structures and helpers of libsla_b200.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/sla_b200.h"
+
+#define SLA_NUM_SMS 148          // B200: 148 SMs (2 dies x 74)
+#define SLA_SCAL_SLOTS 512       // device scalar slots per ctx
+#define SLA_MAX_KRYLOV 384       // max Arnoldi / GMRES basis size (H column lives in scal[S_HCOL..])
+#define SLA_MAX_PARTIALS (1 << 20)
+
+// device scalar slots (doubles living in ctx->scal)
+enum {
+  S_RHO = 0, S_D1, S_ALPHA, S_D3, S_D4, S_OMEGA, S_D5, S_BETA, S_RES2, S_TMP0, S_TMP1, S_TMP2, S_NRM,
+  S_RR, S_PP, S_RHO_NEW, S_INVN, S_HCOL = 64 /* .. S_HCOL + SLA_MAX_KRYLOV + 1 : one Hessenberg column */
+};
+
+struct sla_ctx {
+  int device;
+  int rank, world;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  double* scal;              // SLA_SCAL_SLOTS device doubles (alpha, omega, beta, dot results ...)
+  double* partials;          // per-CTA partial sums for grid reductions (SLA_MAX_PARTIALS * 4 doubles)
+  unsigned int* counter;     // "last block" tickets, one per reduction site
+  double* h_scal;            // pinned host mirror for scalar read-back
+  int64_t launches;
+  void* nccl;                // ncclComm_t when world > 1
+  struct sla_vec *scratch_x, *scratch_y;   // device staging for the host-pointer entry points
+  const void* scal_owner;    // Krylov state whose recurrence scalars currently live in scal[]
+  char err[512];
+};
+
+struct sla_vec {
+  sla_ctx* ctx;
+  int64_t n;
+  double* d;
+  uint64_t version;          // bumped on every write through the API (invalidates cached dots)
+  bool owns;
+};
+
+struct sla_csr {
+  sla_ctx* ctx;
+  int64_t m, n, nnz;
+  int32_t* row_ptr;          // m + 1
+  int32_t* col;              // nnz, padded to a multiple of the tile size
+  double* val;               // nnz, padded
+  int32_t* tile_row;         // ntiles + 1 : first row whose start offset lies in the tile
+  int ntiles;
+  sla_csr* T;                // cached transpose for (<#) / CGNE
+  int is_diag;               // -1 unknown, 0 / 1
+};
+
+struct sla_dense {
+  sla_ctx* ctx;
+  int64_t rows, cols, ld;    // column-major; ld = leading dimension (rows rounded up to 16 doubles)
+  double* d;
+};
+
+struct sla_krylov {
+  sla_ctx* ctx;
+  int kind;                  // SLA_BICGSTAB_ / SLA_CGS_ / SLA_CGNE_
+  int64_t n;
+  sla_vec *x, *r, *p, *u;    // state record
+  sla_vec *t0, *t1, *t2;     // work vectors (aap, s, aas ...)
+  // cached rho = r <.> r0hat from the previous step, valid while nobody touched r or r0hat
+  bool rho_valid;
+  const sla_vec* rho_r0hat;
+  uint64_t rho_r0hat_version, rho_r_version;
+};
+
+static inline sla_status sla_fail(sla_ctx* c, sla_status s, const char* msg) {
+  if (c) snprintf(c->err, sizeof(c->err), "%s", msg);
+  return s;
+}
+
+#define SLA_CUDA(ctx, call)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), "CUDA error %s at %s:%d (%s)",       \
+                        cudaGetErrorString(_e), __FILE__, __LINE__, #call);                  \
+      return SLA_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define SLA_TRY(call)                       \
+  do {                                      \
+    sla_status _s = (call);                 \
+    if (_s != SLA_OK) return _s;            \
+  } while (0)
+
+#define SLA_LAUNCH_CHECK(ctx)               \
+  do {                                      \
+    (ctx)->launches++;                      \
+    SLA_CUDA(ctx, cudaGetLastError());      \
+  } while (0)
+
+// ---- device helpers -----------------------------------------------------------------------
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.  smem: NV * 32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) smem[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = lane < nwarp ? smem[k * 32 + lane] : 0.0;
+      v[k] = warp_sum(t);
+    }
+  }
+}
+
+// Scalar post-processing run by the last CTA of a grid reduction, after the sums are final.
+enum {
+  FIN_STORE = 0,       // scal[dst + k] = sum_k
+  FIN_BICG_ALPHA,      // d1 = sum0 ; alpha = rho / d1
+  FIN_BICG_OMEGA,      // d3 = sum0, d4 = sum1 ; omega = d3 / d4
+  FIN_BICG_BETA,       // d5 = sum0 ; beta = d5 / rho * alpha / omega ; rho = d5
+  FIN_CGS_BETA,        // d = sum0 ; beta = d / rho ; rho = d
+  FIN_CGNE_ALPHA,      // rr = sum0, pp = sum1 ; alpha = rr / pp
+  FIN_CGNE_BETA,       // rr1 = sum0 ; beta = rr1 / rr ; rr = rr1
+  FIN_NORM_INV         // nrm = sqrt(sum0) ; invn = 1 / nrm
+};
+
+__device__ __forceinline__ void finalize_scalars(int fin, int dst, double* scal, const double* sum, int nv) {
+  switch (fin) {
+    case FIN_STORE:
+      for (int k = 0; k < nv; ++k) scal[dst + k] = sum[k];
+      break;
+    case FIN_BICG_ALPHA:                       // alphaj = (r <.> r0hat) / (aap <.> r0hat)   Sparse.hs:974
+      scal[S_D1] = sum[0];
+      scal[S_ALPHA] = scal[S_RHO] / sum[0];
+      break;
+    case FIN_BICG_OMEGA:                       // omegaj = (aasj <.> sj) / (aasj <.> aasj)   Sparse.hs:977
+      scal[S_D3] = sum[0]; scal[S_D4] = sum[1];
+      scal[S_OMEGA] = sum[0] / sum[1];
+      break;
+    case FIN_BICG_BETA:                        // betaj = (rj1 <.> r0hat)/(r <.> r0hat) * alphaj / omegaj   Sparse.hs:980
+      scal[S_D5] = sum[0];
+      scal[S_BETA] = sum[0] / scal[S_RHO] * scal[S_ALPHA] / scal[S_OMEGA];
+      scal[S_RHO] = sum[0];
+      break;
+    case FIN_CGS_BETA:                         // betaj = (rj1 `dot` rhat) / (r `dot` rhat)   Sparse.hs:937
+      scal[S_BETA] = sum[0] / scal[S_RHO];
+      scal[S_RHO] = sum[0];
+      break;
+    case FIN_CGNE_ALPHA:                       // alphai = (r `dot` r) / (p `dot` p)   Sparse.hs:874
+      scal[S_RR] = sum[0]; scal[S_PP] = sum[1];
+      scal[S_ALPHA] = sum[0] / sum[1];
+      break;
+    case FIN_CGNE_BETA:                        // beta = (r1 `dot` r1) / (r `dot` r)   Sparse.hs:877
+      scal[S_BETA] = sum[0] / scal[S_RR];
+      scal[S_RR] = sum[0];
+      break;
+    case FIN_NORM_INV:                         // norm2 = sqrt (norm2Sq) ; recip   SpVector.hs:125-128, Class.hs:94-95
+      scal[S_NRM] = sqrt(sum[0]);
+      scal[S_INVN] = 1.0 / scal[S_NRM];
+      break;
+  }
+}
+
+// Deterministic grid reduction: every CTA writes its NV partials, takes a ticket; the last CTA sums all
+// partials in a fixed order (thread-strided sequential, then the block tree) and post-processes scalars.
+// Must be called by all threads of every CTA.  `mine` holds this CTA's sums in thread 0.
+template <int NV>
+__device__ __forceinline__ void grid_reduce_finish(double (&mine)[NV], double* partials, unsigned int* counter,
+                                                   double* scal, int fin, int dst, double* smem) {
+  __shared__ bool is_last;
+  const unsigned int nblk = gridDim.x;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[(size_t)k * nblk + blockIdx.x] = mine[k];
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == nblk - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    acc[k] = 0.0;
+    const volatile double* p = partials + (size_t)k * nblk;
+    for (unsigned int i = threadIdx.x; i < nblk; i += blockDim.x) acc[k] += p[i];
+  }
+  __syncthreads();
+  block_sum<NV>(acc, smem);
+  if (threadIdx.x == 0) {
+    finalize_scalars(fin, dst, scal, acc, NV);
+    *counter = 0u;
+  }
+}
+
+// internal entry points shared between translation units
+sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi,
+                           const double* u0, const double* u1, int fin, int dst);
+sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A);
+sla_status sla_csr_alloc(sla_ctx* c, int64_t m, int64_t n, int64_t nnz, sla_csr** out);
+sla_status sla_vec_alloc(sla_ctx* c, int64_t n, sla_vec** out);
+sla_status sla_read_scalars(sla_ctx* c, int first, int count, double* host_out);
+
+// SpMV epilogues
+enum {
+  EPI_NONE = 0,
+  EPI_DOT1,      // sum0 = y . u0
+  EPI_DOT2_YY,   // sum0 = y . u0 ; sum1 = y . y
+  EPI_RESNORM    // sum0 = sum (y - u0)^2 ; y is NOT stored (true-residual check, Sparse.hs:1041)
+};
+
+#define SLA_SPMV_TILE 2048

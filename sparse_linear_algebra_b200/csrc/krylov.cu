@@ -1,0 +1,572 @@
+// krylov.cu — the Krylov layer of the hot path: bicgsInit/bicgstabStep, cgsInit/cgsStep, cgneInit/cgneStep,
+// linSolve0, arnoldi (src/Numeric/LinearAlgebra/Sparse.hs:630-667, 855-981, 1016-1072) and a restarted
+// GMRES built on the same Arnoldi kernels.  Every step is a fixed sequence of SpMV launches (with fused dot
+// epilogues) and fused elementwise kernels; alpha / omega / beta are computed on the device by the last CTA
+// of each reduction and never visit the host.
+#include "blas1.cuh"
+
+#include <math.h>
+#include <new>
+#include <vector>
+
+// ---- state records -----------------------------------------------------------------------------------
+
+static sla_status krylov_alloc(sla_ctx* c, int kind, int64_t n, bool need_u, sla_krylov** out) {
+  sla_krylov* st = new (std::nothrow) sla_krylov();
+  if (!st) return sla_fail(c, SLA_ERR_ALLOC, "krylov alloc");
+  memset(st, 0, sizeof(*st));
+  st->ctx = c; st->kind = kind; st->n = n;
+  sla_status s = SLA_OK;
+  sla_vec** all[] = {&st->x, &st->r, &st->p, &st->t0, &st->t1, &st->t2};
+  for (auto v : all) if (s == SLA_OK) s = sla_vec_alloc(c, n, v);
+  if (s == SLA_OK && need_u) s = sla_vec_alloc(c, n, &st->u);
+  if (s != SLA_OK) { sla_krylov_free(st); return s; }
+  *out = st;
+  return SLA_OK;
+}
+
+extern "C" void sla_krylov_free(sla_krylov* st) {
+  if (!st) return;
+  if (st->ctx && st->ctx->scal_owner == st) st->ctx->scal_owner = nullptr;
+  sla_vec_free(st->x); sla_vec_free(st->r); sla_vec_free(st->p); sla_vec_free(st->u);
+  sla_vec_free(st->t0); sla_vec_free(st->t1); sla_vec_free(st->t2);
+  delete st;
+}
+
+static const sla_vec* krylov_field(const sla_krylov* st, int field) {
+  switch (field) {
+    case SLA_FIELD_X: return st->x;
+    case SLA_FIELD_R: return st->r;
+    case SLA_FIELD_P: return st->p;
+    case SLA_FIELD_U: return st->u;
+  }
+  return nullptr;
+}
+
+extern "C" sla_status sla_krylov_view(sla_ctx* c, const sla_krylov* st, int field, const sla_vec** view) {
+  if (!c || !st || !view) return SLA_ERR_INVALID;
+  const sla_vec* v = krylov_field(st, field);
+  if (!v) return sla_fail(c, SLA_ERR_INVALID, "krylov_view: this record has no such field");
+  *view = v;
+  return SLA_OK;
+}
+
+extern "C" sla_status sla_krylov_get(sla_ctx* c, const sla_krylov* st, int field, double* host_out) {
+  const sla_vec* v = nullptr;
+  SLA_TRY(sla_krylov_view(c, st, field, &v));
+  return sla_vec_to_host(c, v, host_out);
+}
+
+static sla_status check_system(sla_ctx* c, const char* who, const sla_csr* A, const sla_vec* b, const sla_vec* x0) {
+  if (!c || !A || !b || !x0) return SLA_ERR_INVALID;
+  if (A->n != x0->n) {       // aa #> x0 : matVec dimension check   Common.hs:248-250
+    snprintf(c->err, sizeof(c->err), "%s: matVec : mismatched dimensions (%lld,%lld)", who, (long long)A->n, (long long)x0->n);
+    return SLA_ERR_SIZE_MISMATCH;
+  }
+  if (A->m != b->n || A->m != A->n) {
+    snprintf(c->err, sizeof(c->err), "%s: Matrix-vector dimensions are incompatible: Matrix is (%lld,%lld), whereas vector is %lld",
+             who, (long long)A->m, (long long)A->n, (long long)b->n);
+    return SLA_ERR_SIZE_MISMATCH;
+  }
+  return SLA_OK;
+}
+
+// r0 = b ^-^ (aa #> x0), copied into up to three records   (bicgsInit / cgsInit / cgneInit)
+static sla_status init_residual(sla_ctx* c, const sla_csr* A, const sla_vec* b, const sla_vec* x0, sla_krylov* st,
+                                double* o0, double* o1, double* o2) {
+  SLA_TRY(sla_vec_copy(c, x0, st->x));
+  SLA_TRY(sla_spmv_launch(c, A, x0->d, st->t0->d, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
+  Ptrs<2> in{{b->d, st->t0->d}};
+  Ptrs<3> out{{o0, o1, o2}};
+  SLA_TRY(ew_launch(c, OpResidInit{}, st->n, in, out, FIN_STORE, S_TMP1));
+  return SLA_OK;
+}
+
+static void bump(sla_vec* v) { if (v) v->version++; }
+
+// rho = r <.> rhat is carried on the device from the previous step while nobody touched r, rhat or the
+// scalar slots; otherwise it is recomputed (the reference recomputes it every step, Sparse.hs:974).
+static sla_status ensure_rho(sla_ctx* c, sla_krylov* st, const sla_vec* rhat) {
+  const bool ok = st->rho_valid && c->scal_owner == st && st->rho_r0hat == rhat &&
+                  st->rho_r0hat_version == rhat->version && st->rho_r_version == st->r->version;
+  if (ok) return SLA_OK;
+  Ptrs<2> in{{st->r->d, rhat->d}}; Ptrs<0> o{};
+  SLA_TRY(ew_launch(c, OpDot{}, st->n, in, o, FIN_STORE, S_RHO));
+  c->scal_owner = st;
+  return SLA_OK;
+}
+
+static void cache_rho(sla_krylov* st, const sla_vec* rhat) {
+  st->rho_valid = true; st->rho_r0hat = rhat;
+  st->rho_r0hat_version = rhat->version; st->rho_r_version = st->r->version;
+}
+
+// ---- BiCGSTAB ------------------------------------------------------------------------------------------
+
+extern "C" sla_status sla_bicgstab_init(sla_ctx* c, const sla_csr* A, const sla_vec* b, const sla_vec* x0, sla_krylov** out) {
+  if (!out) return SLA_ERR_INVALID;
+  *out = nullptr;
+  SLA_TRY(check_system(c, "bicgsInit", A, b, x0));
+  sla_krylov* st = nullptr;
+  SLA_TRY(krylov_alloc(c, SLA_BICGSTAB_, A->m, false, &st));
+  sla_status s = init_residual(c, A, b, x0, st, st->r->d, st->p->d, st->p->d);   // BICGSTAB x0 r0 r0
+  if (s != SLA_OK) { sla_krylov_free(st); return s; }
+  *out = st;
+  return SLA_OK;
+}
+
+extern "C" sla_status sla_bicgstab_step(sla_ctx* c, const sla_csr* A, const sla_vec* r0hat, sla_krylov* st) {
+  if (!c || !A || !r0hat || !st || st->kind != SLA_BICGSTAB_) return SLA_ERR_INVALID;
+  if (A->m != st->n || A->n != st->n || r0hat->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "bicgstabStep: dimensions differ");
+  const int64_t n = st->n;
+  double *x = st->x->d, *r = st->r->d, *p = st->p->d, *aap = st->t0->d, *s = st->t1->d, *aas = st->t2->d;
+  SLA_TRY(ensure_rho(c, st, r0hat));
+  // aap = aa #> p ; alphaj = (r <.> r0hat) / (aap <.> r0hat)
+  SLA_TRY(sla_spmv_launch(c, A, p, aap, EPI_DOT1, r0hat->d, nullptr, FIN_BICG_ALPHA, 0));
+  // sj = r ^-^ (alphaj .* aap)
+  { Ptrs<2> in{{r, aap}}; Ptrs<1> o{{s}}; OpBicgS op; op.alpha = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
+  // aasj = aa #> sj ; omegaj = (aasj <.> sj) / (aasj <.> aasj)
+  SLA_TRY(sla_spmv_launch(c, A, s, aas, EPI_DOT2_YY, s, nullptr, FIN_BICG_OMEGA, 0));
+  // xj1, rj1 ; betaj = (rj1 <.> r0hat)/(r <.> r0hat) * alphaj / omegaj
+  { Ptrs<5> in{{x, p, s, aas, r0hat->d}}; Ptrs<2> o{{x, r}}; OpBicgXR op; op.alpha = op.omega = 0;
+    SLA_TRY(ew_launch(c, op, n, in, o, FIN_BICG_BETA, 0)); }
+  // pj1 = rj1 ^+^ (betaj .* (p ^-^ (omegaj .* aap)))
+  { Ptrs<3> in{{r, p, aap}}; Ptrs<1> o{{p}}; OpBicgP op; op.beta = op.omega = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
+  bump(st->x); bump(st->r); bump(st->p);
+  cache_rho(st, r0hat);
+  return SLA_OK;
+}
+
+// ---- CGS -----------------------------------------------------------------------------------------------
+
+extern "C" sla_status sla_cgs_init(sla_ctx* c, const sla_csr* A, const sla_vec* b, const sla_vec* x0, sla_krylov** out) {
+  if (!out) return SLA_ERR_INVALID;
+  *out = nullptr;
+  SLA_TRY(check_system(c, "cgsInit", A, b, x0));
+  sla_krylov* st = nullptr;
+  SLA_TRY(krylov_alloc(c, SLA_CGS_, A->m, true, &st));
+  sla_status s = init_residual(c, A, b, x0, st, st->r->d, st->p->d, st->u->d);   // CGS x0 r0 r0 r0
+  if (s != SLA_OK) { sla_krylov_free(st); return s; }
+  *out = st;
+  return SLA_OK;
+}
+
+extern "C" sla_status sla_cgs_step(sla_ctx* c, const sla_csr* A, const sla_vec* rhat, sla_krylov* st) {
+  if (!c || !A || !rhat || !st || st->kind != SLA_CGS_) return SLA_ERR_INVALID;
+  if (A->m != st->n || A->n != st->n || rhat->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgsStep: dimensions differ");
+  const int64_t n = st->n;
+  double *x = st->x->d, *r = st->r->d, *p = st->p->d, *u = st->u->d, *t0 = st->t0->d, *q = st->t1->d, *upq = st->t2->d;
+  SLA_TRY(ensure_rho(c, st, rhat));
+  // aap = aa #> p ; alphaj = (r `dot` rhat) / (aap `dot` rhat)
+  SLA_TRY(sla_spmv_launch(c, A, p, t0, EPI_DOT1, rhat->d, nullptr, FIN_BICG_ALPHA, 0));
+  // q = u ^-^ (alphaj .* aap) ; xj1 = x ^+^ (alphaj .* (u ^+^ q))
+  { Ptrs<3> in{{u, t0, x}}; Ptrs<3> o{{q, upq, x}}; OpCgsQ op; op.alpha = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
+  // aa #> (u ^+^ q)
+  SLA_TRY(sla_spmv_launch(c, A, upq, t0, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
+  // rj1 = r ^-^ (alphaj .* ...) ; betaj = (rj1 `dot` rhat) / (r `dot` rhat)
+  { Ptrs<3> in{{r, t0, rhat->d}}; Ptrs<1> o{{r}}; OpCgsR op; op.alpha = 0; SLA_TRY(ew_launch(c, op, n, in, o, FIN_CGS_BETA, 0)); }
+  // uj1 = rj1 ^+^ (betaj .* q) ; pj1 = uj1 ^+^ (betaj .* (q ^+^ (betaj .* p)))
+  { Ptrs<3> in{{r, q, p}}; Ptrs<2> o{{u, p}}; OpCgsUP op; op.beta = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
+  bump(st->x); bump(st->r); bump(st->p); bump(st->u);
+  cache_rho(st, rhat);
+  return SLA_OK;
+}
+
+// ---- CGNE ----------------------------------------------------------------------------------------------
+
+static sla_status ensure_transpose(sla_ctx* c, const sla_csr* A) {
+  if (A->T) return SLA_OK;
+  sla_csr* t = nullptr;
+  SLA_TRY(sla_csr_transpose(c, A, &t));   // the reference re-transposes every step (Sparse.hs:878); built once here
+  const_cast<sla_csr*>(A)->T = t;
+  return SLA_OK;
+}
+
+extern "C" sla_status sla_cgne_init(sla_ctx* c, const sla_csr* A, const sla_vec* b, const sla_vec* x0, sla_krylov** out) {
+  if (!out) return SLA_ERR_INVALID;
+  *out = nullptr;
+  SLA_TRY(check_system(c, "cgneInit", A, b, x0));
+  SLA_TRY(ensure_transpose(c, A));
+  sla_krylov* st = nullptr;
+  SLA_TRY(krylov_alloc(c, SLA_CGNE_, A->m, false, &st));
+  sla_status s = init_residual(c, A, b, x0, st, st->r->d, st->t1->d, st->t1->d);
+  // p0 = transposeSM aa #> r0
+  if (s == SLA_OK) s = sla_spmv_launch(c, A->T, st->r->d, st->p->d, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0);
+  if (s != SLA_OK) { sla_krylov_free(st); return s; }
+  *out = st;
+  return SLA_OK;
+}
+
+extern "C" sla_status sla_cgne_step(sla_ctx* c, const sla_csr* A, sla_krylov* st) {
+  if (!c || !A || !st || st->kind != SLA_CGNE_) return SLA_ERR_INVALID;
+  if (A->m != st->n || A->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgneStep: dimensions differ");
+  SLA_TRY(ensure_transpose(c, A));
+  const int64_t n = st->n;
+  double *x = st->x->d, *r = st->r->d, *p = st->p->d, *ap = st->t0->d, *atr = st->t1->d;
+  c->scal_owner = st;
+  // alphai = (r `dot` r) / (p `dot` p)
+  { Ptrs<2> in{{r, p}}; Ptrs<0> o{}; SLA_TRY(ew_launch(c, OpSelfDot2{}, n, in, o, FIN_CGNE_ALPHA, 0)); }
+  SLA_TRY(sla_spmv_launch(c, A, p, ap, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
+  // x1 = x ^+^ (alphai .* p) ; r1 = r ^-^ (alphai .* (aa #> p)) ; beta = (r1 `dot` r1) / (r `dot` r)
+  { Ptrs<4> in{{x, p, r, ap}}; Ptrs<2> o{{x, r}}; OpCgneXR op; op.alpha = 0; SLA_TRY(ew_launch(c, op, n, in, o, FIN_CGNE_BETA, 0)); }
+  // p1 = transpose aa #> r1 ^+^ (beta .* p)
+  SLA_TRY(sla_spmv_launch(c, A->T, r, atr, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
+  { Ptrs<2> in{{atr, p}}; Ptrs<1> o{{p}}; OpCgneP op; op.beta = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
+  bump(st->x); bump(st->r); bump(st->p);
+  return SLA_OK;
+}
+
+// ---- linSolve0 -----------------------------------------------------------------------------------------
+
+extern "C" void sla_solve_opts_default(sla_solve_opts* o) {
+  if (!o) return;
+  o->max_iters = 200; o->tol_abs = 1e-6; o->tol_rel = 1e-4; o->true_residual = 1; o->check_every = 1;
+}
+
+static sla_status residual_norm(sla_ctx* c, const sla_csr* A, const sla_vec* x, const sla_vec* b, double* out) {
+  // norm2 ((aa #> x) ^-^ b) with the SpMV, the subtraction and the sum of squares in one kernel   Sparse.hs:1041
+  SLA_TRY(sla_spmv_launch(c, A, x->d, nullptr, EPI_RESNORM, b->d, nullptr, FIN_STORE, S_RES2));
+  double r2 = 0;
+  SLA_TRY(sla_read_scalars(c, S_RES2, 1, &r2));
+  *out = sqrt(r2);
+  return SLA_OK;
+}
+
+extern "C" sla_status sla_linsolve0(sla_ctx* c, int method, const sla_csr* A, const sla_vec* b, const sla_vec* x0,
+                                    const sla_solve_opts* opts_in, sla_vec* x, int* iters, double* resnorm) {
+  if (!c || !A || !b || !x0 || !x) return SLA_ERR_INVALID;
+  sla_solve_opts o;
+  sla_solve_opts_default(&o);
+  if (opts_in) o = *opts_in;
+  if (o.max_iters <= 0) o.max_iters = 200;
+  if (o.check_every <= 0) o.check_every = 1;
+  if (iters) *iters = 0;
+  if (resnorm) *resnorm = 0.0;
+  if (A->m != b->n) {                         // | m /= nb = throwM (MatVecSizeMismatchException "linSolve0" dm nb)   :1022
+    snprintf(c->err, sizeof(c->err), "linSolve0 : Matrix-vector dimensions are incompatible: Matrix is (%lld,%lld) , whereas vector is %lld",
+             (long long)A->m, (long long)A->n, (long long)b->n);
+    return SLA_ERR_SIZE_MISMATCH;
+  }
+  if (x->n != A->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "linSolve0 : output vector has the wrong dimension");
+  int diag = 0;
+  SLA_TRY(sla_csr_is_diagonal(c, A, &diag));
+  if (diag) {                                 // isDiagonalSM aa' = return $ reciprocal aa' #> b'   :1024-1025
+    Ptrs<2> in{{A->val, b->d}}; Ptrs<1> out{{x->d}};
+    SLA_TRY(ew_launch(c, OpDiagSolve{}, A->m, in, out));
+    x->version++;
+    return SLA_OK;
+  }
+  if (method != SLA_BICGSTAB_ && method != SLA_CGS_ && method != SLA_CGNE_) {   // IterE   :1031
+    const char* nm = method == SLA_GMRES_ ? "GMRES_" : method == SLA_BCG_ ? "BCG_" : "?";
+    snprintf(c->err, sizeof(c->err), "linSolve0 : Only BICGSTAB_, CGS_, and CGNE_ are implemented, got: %s", nm);
+    return SLA_ERR_UNSUPPORTED_METHOD;
+  }
+  SLA_TRY(check_system(c, "linSolve0", A, b, x0));
+  const int64_t n = A->m;
+  // r0hat = b ^-^ (aa #> x0) ; tol = max tolAbs (tolRel * norm2 r0hat)   :1032-1037
+  sla_vec* r0hat = nullptr;
+  SLA_TRY(sla_vec_alloc(c, n, &r0hat));
+  sla_krylov* st = nullptr;
+  sla_status s = method == SLA_BICGSTAB_ ? sla_bicgstab_init(c, A, b, x0, &st)
+               : method == SLA_CGS_      ? sla_cgs_init(c, A, b, x0, &st)
+                                         : sla_cgne_init(c, A, b, x0, &st);
+  double r0norm = 0, res = 0;
+  if (s == SLA_OK) s = sla_vec_copy(c, st->r, r0hat);          // same arithmetic as bicgsInit's r0
+  if (s == SLA_OK) s = sla_norm2(c, r0hat, &r0norm);
+  const double tol = o.tol_abs > o.tol_rel * r0norm ? o.tol_abs : o.tol_rel * r0norm;
+  int it = 0;
+  while (s == SLA_OK && it < o.max_iters) {                    // runIter   :1043-1052
+    s = method == SLA_BICGSTAB_ ? sla_bicgstab_step(c, A, r0hat, st)
+      : method == SLA_CGS_      ? sla_cgs_step(c, A, r0hat, st)
+                                : sla_cgne_step(c, A, st);
+    if (s != SLA_OK) break;
+    ++it;
+    if (it % o.check_every == 0 || it == o.max_iters) {
+      if (o.true_residual) s = residual_norm(c, A, st->x, b, &res);
+      else { s = sla_norm2(c, st->r, &res); }
+      if (s != SLA_OK) break;
+      if (res <= tol) break;                                   // NaN <= tol is False: runs to max_iters like the reference
+    }
+  }
+  if (s == SLA_OK) s = sla_vec_copy(c, st->x, x);
+  if (s == SLA_OK) s = sla_sync(c);
+  if (iters) *iters = it;
+  if (resnorm) *resnorm = res;
+  sla_krylov_free(st);
+  sla_vec_free(r0hat);
+  return s;
+}
+
+extern "C" sla_status sla_linsolve0_host(sla_ctx* c, int method, const sla_csr* A, const double* b_host, const double* x0_host,
+                                         const sla_solve_opts* opts, double* x_host, int* iters, double* resnorm) {
+  if (!c || !A || !b_host || !x0_host || !x_host) return SLA_ERR_INVALID;
+  sla_vec *b = nullptr, *x0 = nullptr, *x = nullptr;
+  sla_status s = sla_vec_from_host(c, A->m, b_host, &b);
+  if (s == SLA_OK) s = sla_vec_from_host(c, A->n, x0_host, &x0);
+  if (s == SLA_OK) s = sla_vec_create(c, A->n, &x);
+  if (s == SLA_OK) s = sla_linsolve0(c, method, A, b, x0, opts, x, iters, resnorm);
+  if (s == SLA_OK) s = sla_vec_to_host(c, x, x_host);
+  sla_vec_free(b); sla_vec_free(x0); sla_vec_free(x);
+  return s;
+}
+
+// ---- Arnoldi -------------------------------------------------------------------------------------------
+
+#define TS_CH 8   // basis columns handled per pass of the tall-skinny kernels
+
+// h[k0 + k] = q_{k0+k} <.> w   for k < nc <= TS_CH        (hhcoli = fmap (`dot` aqi) qv, Sparse.hs:655)
+__global__ void __launch_bounds__(EW_THREADS)
+tsmv_t_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int k0, int nc, const double* __restrict__ w,
+              double* scal, double* partials, unsigned int* counter) {
+  __shared__ double red[TS_CH * 32];
+  double acc[TS_CH];
+#pragma unroll
+  for (int k = 0; k < TS_CH; ++k) acc[k] = 0.0;
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = gtid; i < n2; i += stride) {
+    const double2 wv = reinterpret_cast<const double2*>(w)[i];
+#pragma unroll
+    for (int k = 0; k < TS_CH; ++k) {
+      if (k < nc) {
+        const double2 q = reinterpret_cast<const double2*>(Q + (int64_t)(k0 + k) * ld)[i];
+        acc[k] += q.x * wv.x;
+        acc[k] += q.y * wv.y;
+      }
+    }
+  }
+  if ((n & 1) && gtid == 0) {
+    for (int k = 0; k < nc; ++k) acc[k] += Q[(int64_t)(k0 + k) * ld + n - 1] * w[n - 1];
+  }
+  block_sum<TS_CH>(acc, red);
+  grid_reduce_finish<TS_CH>(acc, partials, counter, scal, FIN_STORE, S_HCOL + k0, red);
+}
+
+// out_i = base_i -/+ (((c_0 q_0i) + c_1 q_1i) + ... + c_{nc-1} q_{nc-1,i}), coefficients in scal[S_HCOL..];
+// SIGN = -1: qipnn = aqi ^-^ foldl' (^+^) zv (zipWith (.*) hhcoli qv), plus sum of squares (Sparse.hs:657-659)
+// SIGN = +1: x = x ^+^ Q y (GMRES update)
+template <int SIGN>
+__global__ void __launch_bounds__(EW_THREADS)
+lincomb_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int nc, const double* base, double* out,
+               double* scal, double* partials, unsigned int* counter, int fin) {
+  __shared__ double coef[SLA_MAX_KRYLOV + 2];
+  __shared__ double red[32];
+  for (int k = threadIdx.x; k < nc; k += blockDim.x) coef[k] = scal[S_HCOL + k];
+  __syncthreads();
+  double acc[1] = {0.0};
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = gtid; i < n2; i += stride) {
+    double2 s;
+    {
+      const double2 q = reinterpret_cast<const double2*>(Q)[i];
+      s.x = __dmul_rn(coef[0], q.x); s.y = __dmul_rn(coef[0], q.y);      // zeroSV ^+^ (h0 .* q0) = h0 .* q0
+    }
+    for (int k = 1; k < nc; ++k) {
+      const double2 q = reinterpret_cast<const double2*>(Q + (int64_t)k * ld)[i];
+      s.x = __dadd_rn(s.x, __dmul_rn(coef[k], q.x));
+      s.y = __dadd_rn(s.y, __dmul_rn(coef[k], q.y));
+    }
+    const double2 b = reinterpret_cast<const double2*>(base)[i];
+    double2 o;
+    o.x = SIGN < 0 ? __dsub_rn(b.x, s.x) : __dadd_rn(b.x, s.x);
+    o.y = SIGN < 0 ? __dsub_rn(b.y, s.y) : __dadd_rn(b.y, s.y);
+    reinterpret_cast<double2*>(out)[i] = o;
+    acc[0] += o.x * o.x + o.y * o.y;
+  }
+  if ((n & 1) && gtid == 0) {
+    const int64_t i = n - 1;
+    double s = __dmul_rn(coef[0], Q[i]);
+    for (int k = 1; k < nc; ++k) s = __dadd_rn(s, __dmul_rn(coef[k], Q[(int64_t)k * ld + i]));
+    const double o = SIGN < 0 ? __dsub_rn(base[i], s) : __dadd_rn(base[i], s);
+    out[i] = o;
+    acc[0] += o * o;
+  }
+  if (SIGN < 0) {
+    block_sum<1>(acc, red);
+    grid_reduce_finish<1>(acc, partials, counter, scal, fin, 0, red);
+  }
+}
+
+static unsigned ts_blocks(int64_t n) {
+  int64_t b = ((n >> 1) + EW_THREADS - 1) / EW_THREADS;
+  if (b < 1) b = 1;
+  if (b > EW_MAX_BLOCKS) b = EW_MAX_BLOCKS;
+  return (unsigned)b;
+}
+
+static sla_status dense_alloc(sla_ctx* c, int64_t rows, int64_t cols, sla_dense** out) {
+  sla_dense* d = new (std::nothrow) sla_dense();
+  if (!d) return sla_fail(c, SLA_ERR_ALLOC, "dense alloc");
+  d->ctx = c; d->rows = rows; d->cols = cols; d->ld = (rows + 15) & ~(int64_t)15; d->d = nullptr;
+  if (d->ld == 0) d->ld = 16;
+  if (cudaMalloc(&d->d, sizeof(double) * (size_t)d->ld * (size_t)(cols > 0 ? cols : 1)) != cudaSuccess) {
+    cudaGetLastError(); delete d;
+    return sla_fail(c, SLA_ERR_ALLOC, "cudaMalloc failed for a dense block");
+  }
+  *out = d;
+  return SLA_OK;
+}
+
+// One Arnoldi step on the device: given basis columns 0..j of Q, append column j+1 and produce column j of H.
+//   aqi = aa #> q_j ; h_k = q_k <.> aqi (k <= j) ; w = aqi - sum_k h_k q_k ; h_{j+1} = norm2 w ; q_{j+1} = w ./ h_{j+1}
+// hcol (host, j + 2 doubles) receives the column.
+static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j, double* w, double* hcol) {
+  const int64_t n = Q->rows, ld = Q->ld;
+  SLA_TRY(sla_spmv_launch(c, A, Q->d + (int64_t)j * ld, w, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
+  const int nq = j + 1;
+  for (int k0 = 0; k0 < nq; k0 += TS_CH) {
+    const int nc = nq - k0 < TS_CH ? nq - k0 : TS_CH;
+    tsmv_t_kernel<<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter);
+    SLA_LAUNCH_CHECK(c);
+  }
+  lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, FIN_NORM_INV);
+  SLA_LAUNCH_CHECK(c);
+  // q_{j+1} = (recip h_{j+1,j}) .* w
+  { Ptrs<1> in{{w}}; Ptrs<1> o{{Q->d + (int64_t)(j + 1) * ld}}; OpScaleDev op; op.slot = S_INVN; op.a = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
+  // read back the column: h_0..h_j from S_HCOL.., h_{j+1} = S_NRM
+  SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + S_HCOL, c->scal + S_HCOL, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
+  SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + S_NRM, c->scal + S_NRM, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < nq; ++k) hcol[k] = c->h_scal[S_HCOL + k];
+  hcol[nq] = c->h_scal[S_NRM];
+  return SLA_OK;
+}
+
+extern "C" sla_status sla_arnoldi(sla_ctx* c, const sla_csr* A, const sla_vec* b, int kn, sla_dense** Qout, double* h_host, int* nmax_out) {
+  if (!c || !A || !b || !Qout || !h_host || !nmax_out) return SLA_ERR_INVALID;
+  *Qout = nullptr; *nmax_out = 0;
+  if (A->n != b->n) {                      // | n == nb ... | otherwise = throwM (MatVecSizeMismatchException "arnoldi" (m,n) nb)   :636-637
+    snprintf(c->err, sizeof(c->err), "arnoldi : Matrix-vector dimensions are incompatible: Matrix is (%lld,%lld) , whereas vector is %lld",
+             (long long)A->m, (long long)A->n, (long long)b->n);
+    return SLA_ERR_SIZE_MISMATCH;
+  }
+  if (A->m != A->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "arnoldi : matrix must be square");
+  if (kn < 2 || kn > SLA_MAX_KRYLOV)       // kn <= 1 never meets `i == kn` and runs to breakdown in the reference; not supported here
+    return sla_fail(c, SLA_ERR_INVALID, "arnoldi : kn must be in [2, 384]");
+  const int64_t n = A->m;
+  sla_dense* Q = nullptr;
+  SLA_TRY(dense_alloc(c, n, kn + 1, &Q));
+  sla_vec* w = nullptr;
+  sla_status s = sla_vec_alloc(c, n, &w);
+  if (s != SLA_OK) { sla_dense_free(Q); return s; }
+  // q0 = normalize2 b   :643
+  {
+    Ptrs<1> in{{b->d}}; Ptrs<0> o0{};
+    s = ew_launch(c, OpNorm2Sq{}, n, in, o0, FIN_NORM_INV, 0);
+    Ptrs<1> o{{Q->d}}; OpScaleDev op; op.slot = S_INVN; op.a = 0;
+    if (s == SLA_OK) s = ew_launch(c, op, n, in, o);
+  }
+  // arnInit is the j = 0 step; modifyUntil then applies the step and tests `i == kn || breakdown`   :639-651
+  for (int z = 0; z < (kn + 1) * kn; ++z) h_host[z] = 0.0;
+  int i = 0;          // columns of H produced so far
+  bool brk = false;
+  double hcol[SLA_MAX_KRYLOV + 2];
+  while (s == SLA_OK) {
+    s = arnoldi_step(c, A, Q, i, w->d, hcol);
+    if (s != SLA_OK) break;
+    for (int k = 0; k <= i + 1; ++k) h_host[(int64_t)i * (kn + 1) + k] = hcol[k];
+    brk = i > 0 && fabs(hcol[i + 1]) <= 1e-12;      // nearZero qipnorm (arnInit itself has no breakdown test)   :666
+    ++i;
+    if (i == kn || brk) break;
+  }
+  sla_vec_free(w);
+  if (s != SLA_OK) { sla_dense_free(Q); return s; }
+  // on breakdown the reference returns H as (nmax+1) x nmax with nmax = i; repack the leading block
+  if (i < kn) {
+    for (int col = 0; col < i; ++col)
+      for (int row = 0; row <= i; ++row) h_host[(int64_t)col * (i + 1) + row] = h_host[(int64_t)col * (kn + 1) + row];
+    Q->cols = i + 1;
+  }
+  *nmax_out = i;
+  *Qout = Q;
+  return brk ? SLA_ERR_BREAKDOWN : SLA_OK;
+}
+
+// ---- GMRES(restart) --------------------------------------------------------------------------------------
+// Restarted GMRES on the Arnoldi kernels above: classical Gram-Schmidt basis, Givens rotations on the host
+// for the (restart+1) x restart least-squares problem, x += Q y on the device.  The reference's own gmres
+// (arnoldi -> qr -> triUpperSolve -> Q y) is commented out (Sparse.hs:837-848); tolerance and iteration-cap
+// conventions follow linSolve0 (Sparse.hs:1034-1037).
+extern "C" sla_status sla_gmres(sla_ctx* c, const sla_csr* A, const sla_vec* b, const sla_vec* x0, int restart,
+                                const sla_solve_opts* opts_in, sla_vec* x, int* iters, double* resnorm) {
+  if (!c || !A || !b || !x0 || !x) return SLA_ERR_INVALID;
+  SLA_TRY(check_system(c, "gmres", A, b, x0));
+  if (restart < 1 || restart > SLA_MAX_KRYLOV) return sla_fail(c, SLA_ERR_INVALID, "gmres : restart must be in [1, 384]");
+  sla_solve_opts o;
+  sla_solve_opts_default(&o);
+  if (opts_in) o = *opts_in;
+  if (o.max_iters <= 0) o.max_iters = 200;
+  const int64_t n = A->m;
+  const int m = restart;
+  sla_dense* Q = nullptr;
+  sla_vec* w = nullptr;
+  SLA_TRY(dense_alloc(c, n, m + 1, &Q));
+  sla_status s = sla_vec_alloc(c, n, &w);
+  if (s == SLA_OK && x != x0) s = sla_vec_copy(c, x0, x);
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), y(m, 0.0);
+  double hcol[SLA_MAX_KRYLOV + 2];
+  int total = 0;
+  double res = 0, tol = 0;
+  bool first = true, done = false;
+  while (s == SLA_OK && !done) {
+    // r = b - A x ; beta = ||r|| ; q0 = r / beta
+    s = sla_spmv_launch(c, A, x->d, w->d, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0);
+    if (s != SLA_OK) break;
+    { Ptrs<2> in{{b->d, w->d}}; Ptrs<3> out{{w->d, w->d, w->d}}; s = ew_launch(c, OpResidInit{}, n, in, out, FIN_NORM_INV, 0); }
+    if (s != SLA_OK) break;
+    { Ptrs<1> in{{w->d}}; Ptrs<1> out{{Q->d}}; OpScaleDev op; op.slot = S_INVN; op.a = 0; s = ew_launch(c, op, n, in, out); }
+    if (s != SLA_OK) break;
+    double beta = 0;
+    s = sla_read_scalars(c, S_NRM, 1, &beta);
+    if (s != SLA_OK) break;
+    res = beta;
+    if (first) { tol = o.tol_abs > o.tol_rel * beta ? o.tol_abs : o.tol_rel * beta; first = false; }
+    if (!(beta > tol) || total >= o.max_iters) break;     // converged on the true residual (or NaN / cap)
+    for (int k = 0; k <= m; ++k) g[k] = 0.0;
+    g[0] = beta;
+    int j = 0;
+    for (; j < m && total < o.max_iters; ++j) {
+      s = arnoldi_step(c, A, Q, j, w->d, hcol);
+      if (s != SLA_OK) break;
+      ++total;
+      for (int k = 0; k < j; ++k) {                        // apply the previous rotations to the new column
+        const double t = cs[k] * hcol[k] + sn[k] * hcol[k + 1];
+        hcol[k + 1] = -sn[k] * hcol[k] + cs[k] * hcol[k + 1];
+        hcol[k] = t;
+      }
+      const double a = hcol[j], bb = hcol[j + 1], d = hypot(a, bb);
+      cs[j] = d == 0.0 ? 1.0 : a / d; sn[j] = d == 0.0 ? 0.0 : bb / d;
+      hcol[j] = cs[j] * a + sn[j] * bb; hcol[j + 1] = 0.0;
+      g[j + 1] = -sn[j] * g[j]; g[j] = cs[j] * g[j];
+      for (int k = 0; k <= j; ++k) H[(size_t)j * (m + 1) + k] = hcol[k];
+      res = fabs(g[j + 1]);
+      if (res <= tol || fabs(bb) <= 1e-12) { ++j; break; }
+    }
+    if (s != SLA_OK) break;
+    // back-substitution R y = g, then x = x + Q[:, 0..j-1] y
+    for (int k = j - 1; k >= 0; --k) {
+      double t = g[k];
+      for (int l = k + 1; l < j; ++l) t -= H[(size_t)l * (m + 1) + k] * y[l];
+      y[k] = t / H[(size_t)k * (m + 1) + k];
+    }
+    if (j > 0) {
+      for (int k = 0; k < j; ++k) c->h_scal[S_HCOL + k] = y[k];
+      cudaMemcpyAsync(c->scal + S_HCOL, c->h_scal + S_HCOL, sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, c->stream);
+      lincomb_kernel<1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, Q->ld, n, j, x->d, x->d, c->scal, c->partials, c->counter, FIN_STORE);
+      c->launches++;
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        s = sla_fail(c, SLA_ERR_CUDA, "gmres: CUDA error in the solution update");
+        break;
+      }
+    }
+    if (total >= o.max_iters) {
+      // report the true residual of the returned iterate
+      s = residual_norm(c, A, x, b, &res);
+      done = true;
+    }
+  }
+  x->version++;
+  if (iters) *iters = total;
+  if (resnorm) *resnorm = res;
+  sla_vec_free(w); sla_dense_free(Q);
+  return s;
+}

@@ -1,0 +1,68 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/sla_b200.h declares, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sla_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sla_[a-z0-9_A-Z]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from sparse_linear_algebra_b200 import _lib
+
+    return _lib
+
+
+def test_header_symbols_exported(lib):
+    L = C.CDLL(lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 50
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/sla_b200.h but not exported by libsla_b200.so"
+
+
+def test_bindings_cover_header(lib):
+    assert sorted(lib.SIGNATURES) == _declared_symbols()
+
+
+def test_no_oracle_in_product():
+    """The product path must never import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "sparse_linear_algebra_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.lower(), f"{f} mentions the oracle"
+
+
+def test_fails_loudly_without_gpu(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import sparse_linear_algebra_b200 as sla
+
+    with pytest.raises(sla.SlaError) as e:
+        sla.Context(0)
+    assert e.value.status == lib.SLA_ERR_CUDA
+    assert "no CPU path" in str(e.value)
+
+
+def test_solve_opts_defaults(lib):
+    L = lib.load()
+    o = lib.SolveOpts()
+    L.sla_solve_opts_default(C.byref(o))
+    # nits = 200, tolAbs = 1e-6, tolRel = 1e-4   (Sparse.hs:1034-1036)
+    assert (o.max_iters, o.tol_abs, o.tol_rel, o.true_residual, o.check_every) == (200, 1e-6, 1e-4, 1, 1)

@@ -1,0 +1,444 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle and the
+reference's own known-answer fixtures.  Run on the B200 box with `pytest -m gpu`.
+
+Tolerances, u = 2^-53:
+  * CSR construction / transpose / elementwise vector ops: BIT-EXACT.
+  * SpMV rows of <= 256 entries: BIT-EXACT (products rounded once, summed in ascending column order from 0,
+    exactly the reference's left fold).  Longer rows: |dy| <= (k + 2) u sum|a_ij x_j|.
+  * dot / norm: |d| <= 64 u sum|x_i y_i| (tree reduction).
+  * Krylov iterates: first steps within 1e-10 relative of the oracle trajectory; same iteration count.
+"""
+import numpy as np
+import pytest
+
+import fixtures as F
+
+pytestmark = pytest.mark.gpu
+U = 2.0 ** -53
+
+
+@pytest.fixture(scope="module")
+def sla():
+    import sparse_linear_algebra_b200 as s
+
+    return s
+
+
+@pytest.fixture(scope="module")
+def o(ora):
+    return ora
+
+
+def dense(sla, fx):
+    return sla.SpMatrix.fromListDenseSM(fx[0], fx[1])
+
+
+def vr(sla, ll):
+    return sla.SpVector.mkSpVR(len(ll), ll)
+
+
+def nearZero(a):
+    return abs(a) <= 1e-12
+
+
+# =============================================================== the reference's own specs, on the device
+
+def test_ref_dot(sla):                                  # LibSpec.hs:45-46
+    tv0 = vr(sla, F.TV0)
+    assert tv0.dot(tv0) == 61
+
+
+def test_ref_transpose_exact(sla):                      # LibSpec.hs:49-50
+    t = dense(sla, F.M1).transpose()
+    e = dense(sla, F.M1T)
+    for a, b in zip(t.toCSR(), e.toCSR()):
+        assert a.tolist() == b.tolist()
+
+
+def test_ref_matvec_vecmat(sla):                        # LibSpec.hs:51-54
+    aa0, x0true = dense(sla, F.AA0), vr(sla, F.X0TRUE)
+    assert (aa0 @ x0true).toDenseListSV().tolist() == [8.0, 18.0]
+    assert aa0.vecMat(x0true).toDenseListSV().tolist() == [11.0, 16.0]
+    assert nearZero(((aa0 @ x0true) - vr(sla, F.B0)).norm2Sq())
+
+
+def test_ref_fromlist_semantics(sla):                   # LibSpec.hs:63-65, 1268 ; SpMatrix.hs:205-224
+    m1p = sla.SpMatrix.fromListSM(*F.M1P)               # duplicate (1,2,4),(1,2,1): last write wins
+    rp, ci, va = m1p.toCSR()
+    assert rp.tolist() == [0, 1, 3] and ci.tolist() == [0, 0, 2] and va.tolist() == [2.0, 3.0, 1.0]
+    with pytest.raises(sla.OutOfBoundsIndexError):
+        sla.SpMatrix.fromListSM((2, 2), [(0, 2, 1.0)])
+    with pytest.raises(sla.OutOfBoundsIndexError):
+        sla.SpMatrix.fromListSM((2, 2), [(-1, 0, 1.0)])
+    v = sla.SpVector.fromListSV(3, [(1, 7.0), (1, 9.0), (5, 1.0)])      # SpVector.hs:275-278
+    assert v.toDenseListSV().tolist() == [0.0, 7.0, 0.0]
+
+
+def test_ref_matvec_dim_mismatch(sla):                  # Common.hs:248-250
+    with pytest.raises(sla.MatVecSizeMismatchException):
+        dense(sla, F.AA0) @ vr(sla, [1, 2, 3])
+
+
+def test_ref_eye_is_diagonal(sla):                      # LibSpec.hs:68-69 ; SpMatrix.hs:411-415
+    e = sla.SpMatrix.eye(10)
+    assert e.nnz == 10 and e.isDiagonalSM()
+    assert not dense(sla, F.AA0).isDiagonalSM()
+    # a stored row with a single OFF-diagonal entry is not diagonal
+    assert not sla.SpMatrix.fromListSM((2, 2), [(0, 1, 1.0), (1, 0, 1.0)]).isDiagonalSM()
+
+
+def test_ref_krylov_init_exact(sla, o):                 # LibSpec.hs:252-257, 265-269
+    aa0, b0, x0 = dense(sla, F.AA0), vr(sla, F.B0), vr(sla, F.X0)
+    r0 = (b0 - (aa0 @ x0)).toDenseListSV()
+    st = sla.bicgsInit(aa0, b0, x0)
+    assert st.r.toDenseListSV().tolist() == r0.tolist() and st.p.toDenseListSV().tolist() == r0.tolist()
+    st = sla.cgsInit(aa0, b0, x0)
+    for f in (st.r, st.p, st.u):
+        assert f.toDenseListSV().tolist() == r0.tolist()
+    # and identical to the oracle's b - A x0
+    ao = o.SpMatrix.fromListDenseSM(*F.AA0)
+    ro = o.SpVector.mkSpVR(2, F.B0) - ao.matVec(o.SpVector.mkSpVR(2, F.X0))
+    assert ro.toDenseListSV().tolist() == r0.tolist()
+
+
+def _check_solver(sla, init, step, aa, b, niter):
+    """checkCGS / checkBiCGSTAB (LibSpec.hs:548-575, 606-632)."""
+    x0 = sla.SpVector.fromListSV(b.dim, [])
+    rhat = b - (aa @ x0)
+    st = init(aa, b, x0)
+    tol = max(1e-6, 1e-4 * st.r.norm2())
+    res = lambda s: ((aa @ s.x) - b).norm2()
+    n = 0
+    while n < niter:
+        st = step(aa, rhat, st)
+        n += 1
+        if res(st) <= tol:
+            break
+    return res(st) <= tol, n, st
+
+
+@pytest.mark.parametrize("solver", ["cgs", "bicgstab"])
+@pytest.mark.parametrize("system", ["aa0", "aa2"])
+def test_ref_solver_converges(sla, solver, system):     # LibSpec.hs:259-262, 276-279
+    aa = dense(sla, F.AA0 if system == "aa0" else F.AA2)
+    b = vr(sla, F.B0 if system == "aa0" else F.B2)
+    init, step = (sla.cgsInit, sla.cgsStep) if solver == "cgs" else (sla.bicgsInit, sla.bicgstabStep)
+    ok, n, _ = _check_solver(sla, init, step, aa, b, 50)
+    assert ok and n <= 50
+
+
+@pytest.mark.parametrize("method", ["BICGSTAB_", "CGS_", "CGNE_"])
+@pytest.mark.parametrize("system", ["aa0", "aa2"])
+def test_ref_linsolve0(sla, o, method, system):         # LibSpec.hs:286-300: ||x - xhat|| <= 1e-12
+    fx, bb, xx = (F.AA0, F.B0, F.X0TRUE) if system == "aa0" else (F.AA2, F.B2, F.X2)
+    aa = dense(sla, fx)
+    n = aa.ncols
+    xhat, iters, _ = sla.linSolve0(getattr(sla, method), aa, vr(sla, bb), sla.SpVector.mkSpVR(n, [0.1] * n), info=True)
+    assert nearZero((vr(sla, xx) - xhat).norm2())
+    # same iteration count as the oracle
+    ao = o.SpMatrix.fromListDenseSM(*fx)
+    _, it_o, _ = o.linSolve0(getattr(o, method), ao, o.SpVector.mkSpVR(n, bb), o.SpVector.mkSpVR(n, [0.1] * n), info=True)
+    assert iters == it_o
+
+
+def test_ref_linsolve0_errors_and_diagonal(sla):        # Sparse.hs:1022, 1024-1025, 1031
+    aa0, b0 = dense(sla, F.AA0), vr(sla, F.B0)
+    x0r = sla.SpVector.mkSpVR(2, [0.1, 0.1])
+    with pytest.raises(sla.IterE) as e:
+        sla.linSolve0(sla.GMRES_, aa0, b0, x0r)
+    assert "Only BICGSTAB_, CGS_, and CGNE_ are implemented, got: GMRES_" in str(e.value)
+    with pytest.raises(sla.IterE):
+        sla.linSolve0(sla.BCG_, aa0, b0, x0r)
+    with pytest.raises(sla.MatVecSizeMismatchException):
+        sla.linSolve0(sla.BICGSTAB_, aa0, vr(sla, [1, 2, 3]), x0r)
+    d = sla.SpMatrix.fromListSM((3, 3), [(0, 0, 2.0), (1, 1, 4.0), (2, 2, 8.0)])
+    x = sla.linSolve0(sla.BCG_, d, vr(sla, [2, 2, 2]), sla.SpVector.zeroSV(3))      # diagonal shortcut precedes the method check
+    assert x.toDenseListSV().tolist() == [1.0, 0.5, 0.25]
+
+
+def test_ref_readme_example(sla):                       # README.md:97, 183-241
+    amat = sla.SpMatrix.fromListSM(*F.AMAT)
+    b = vr(sla, F.AMAT_B)
+    x = sla.linSolve0(sla.BICGSTAB_, amat, b, sla.SpVector.fromListSV(3, []))
+    np.testing.assert_allclose(x.toDenseListSV(), F.AMAT_X, atol=1e-5)
+    np.testing.assert_allclose((amat @ x).toDenseListSV(), F.AMAT_B, atol=1e-5)
+    xg = sla.backslash(amat, b)                         # aa <\> b (GMRES)
+    np.testing.assert_allclose(xg.toDenseListSV(), F.AMAT_X, atol=1e-5)
+
+
+@pytest.mark.parametrize("which,kn", [("aa4", 3), ("tm7", 4)])
+def test_ref_arnoldi(sla, o, which, kn):                # LibSpec.hs:226-232, checkArnoldi :638-653
+    if which == "aa4":
+        aa, ao = dense(sla, F.AA4), o.SpMatrix.fromListDenseSM(*F.AA4)
+    else:
+        aa, ao = sla.SpMatrix.fromListSM(*F.tm7_triples()), o.SpMatrix.fromListSM(*F.tm7_triples())
+    n = aa.nrows
+    Qd, H, brk = sla.arnoldi(aa, sla.SpVector.onesSV(n), kn)
+    Q = Qd.toHost()
+    A = aa.toDense()
+    assert H.shape[0] == H.shape[1] + 1 and Q.shape == (n, H.shape[0])
+    assert np.linalg.norm(A @ Q[:, :-1] - Q @ H) <= 1e-12
+    Qo, Ho = o.arnoldi(ao, o.SpVector.onesSV(n), kn)
+    assert Qo.shape == Q.shape and Ho.shape == H.shape
+    # compare with the oracle where the process is well conditioned (before a breakdown column)
+    good = H.shape[1] if not brk else H.shape[1] - 1
+    np.testing.assert_allclose(H[:, :good], Ho[:, :good], atol=1e-9)
+
+
+# =============================================================== oracle parity on seeded inputs
+
+def _rand_coo(rng, m, n, k, long_rows=()):
+    i = rng.integers(0, m, k)
+    j = rng.integers(0, n, k)
+    for r, ln in long_rows:
+        i = np.concatenate([i, np.full(ln, r)])
+        j = np.concatenate([j, rng.choice(n, ln, replace=False)])
+    v = rng.standard_normal(i.size)
+    return i, j, v
+
+
+@pytest.mark.parametrize("seed,m,n,k", [(0, 1, 1, 1), (1, 7, 5, 0), (2, 50, 40, 300), (3, 3000, 2500, 20000),
+                                        (4, 20000, 20000, 150000), (5, 100, 100000, 5000)])
+def test_coo_to_csr_and_transpose_bit_exact(sla, o, seed, m, n, k):
+    rng = np.random.default_rng(seed)
+    i, j, v = _rand_coo(rng, m, n, k)
+    A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+    Ao = o.SpMatrix.fromCOO((m, n), i, j, v)
+    rp, ci, va = A.toCSR()
+    rpo, cio, vao = Ao.toCSR()
+    assert rp.tolist() == rpo.tolist() and ci.tolist() == cio.tolist()
+    assert va.tobytes() == vao.tobytes()
+    rp, ci, va = A.transpose().toCSR()
+    rpo, cio, vao = Ao.transpose().toCSR()
+    assert rp.tolist() == rpo.tolist() and ci.tolist() == cio.tolist()
+    assert va.tobytes() == vao.tobytes()
+    # transpose is an involution, bit for bit
+    rp2, ci2, va2 = A.transpose().transpose().toCSR()
+    rp1, ci1, va1 = A.toCSR()
+    assert rp2.tolist() == rp1.tolist() and ci2.tolist() == ci1.tolist() and va2.tobytes() == va1.tobytes()
+
+
+@pytest.mark.parametrize("seed,m,n,k", [(10, 1, 1, 1), (11, 9, 9, 0), (12, 64, 64, 500), (13, 5000, 4000, 40000),
+                                        (14, 30000, 30000, 400000), (15, 300, 5000, 60000)])
+def test_spmv_bit_exact_short_rows(sla, o, seed, m, n, k):
+    """Rows of <= 256 entries: identical bits to the oracle's sequential left fold; includes empty rows, rows
+    straddling tile boundaries (nnz > 2048) and matrices smaller than one tile."""
+    rng = np.random.default_rng(seed)
+    i, j, v = _rand_coo(rng, m, n, k)
+    A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+    Ao = o.SpMatrix.fromCOO((m, n), i, j, v)
+    rp = A.toCSR()[0]
+    assert np.diff(rp).max(initial=0) <= 256
+    x = rng.standard_normal(n)
+    y = (A @ sla.SpVector.mkSpVR(n, x)).toDenseListSV()
+    yo = Ao.matVec(o.SpVector.mkSpVR(n, x)).toDenseListSV()
+    assert y.tobytes() == yo.tobytes()
+    yh = A.matVecHost(x)                                 # host-buffer entry point, same bits
+    assert yh.tobytes() == yo.tobytes()
+    # (<#) through the cached transpose
+    xt = rng.standard_normal(m)
+    z = A.vecMat(sla.SpVector.mkSpVR(m, xt)).toDenseListSV()
+    zo = Ao.vecMat(o.SpVector.mkSpVR(m, xt)).toDenseListSV()
+    assert z.tobytes() == zo.tobytes()
+
+
+def test_spmv_long_rows_within_bound(sla, o):
+    """Rows longer than 256 entries (warp path) and longer than a tile: componentwise bound (k+2) u sum|a x|."""
+    rng = np.random.default_rng(20)
+    m, n = 400, 20000
+    i, j, v = _rand_coo(rng, m, n, 3000, long_rows=[(3, 257), (77, 1000), (78, 2049), (200, 9000), (399, 5000)])
+    A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+    Ao = o.SpMatrix.fromCOO((m, n), i, j, v)
+    x = rng.standard_normal(n)
+    y = (A @ sla.SpVector.mkSpVR(n, x)).toDenseListSV()
+    yo = Ao.matVec(o.SpVector.mkSpVR(n, x)).toDenseListSV()
+    rp, ci, va = A.toCSR()
+    lens = np.diff(rp)
+    absum = np.array([np.abs(va[rp[r]:rp[r + 1]] * x[ci[rp[r]:rp[r + 1]]]).sum() for r in range(m)])
+    short = lens <= 256
+    assert y[short].tobytes() == yo[short].tobytes()
+    assert np.all(np.abs(y - yo) <= (lens + 2) * U * absum)
+    assert (~short).sum() == 5
+
+
+def test_synthetic_generators_match_oracle(sla, o):
+    for kind, n, k, band in ((sla.GEN_UNIFORM, 3000, 32, 0), (sla.GEN_BANDED, 3000, 16, 100),
+                             (sla.GEN_LAPLACE2D, 64 * 64, 5, 64), (sla.GEN_UNIFORM, 40, 64, 0)):
+        A = sla.SpMatrix.generate(kind, n, k, 0x5EED0001, band)
+        Ao = o.SpMatrix.synth(kind, n, k, 0x5EED0001, band)
+        rp, ci, va = A.toCSR()
+        rpo, cio, vao = Ao.toCSR()
+        assert rp.tolist() == rpo.tolist() and ci.tolist() == cio.tolist() and va.tobytes() == vao.tobytes()
+    x = sla.SpVector.generate(1000, 7).toDenseListSV()
+    assert x.tobytes() == o.SpVector.synth(7, 1000).toDenseListSV().tobytes()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1000, 1001, 1 << 20, (1 << 20) + 7])
+def test_vector_ops(sla, o, n):
+    rng = np.random.default_rng(n)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    va, vb = sla.SpVector.mkSpVR(n, a), sla.SpVector.mkSpVR(n, b)
+    # elementwise: bit-exact
+    assert (va + vb).toDenseListSV().tobytes() == (a + b).tobytes()
+    assert (va - vb).toDenseListSV().tobytes() == (a - b).tobytes()
+    assert (0.37 * va).toDenseListSV().tobytes() == (0.37 * a).tobytes()
+    assert (va / 3.0).toDenseListSV().tobytes() == ((1.0 / 3.0) * a).tobytes()
+    assert vb.axpy(-1.7, va).toDenseListSV().tobytes() == (b + (-1.7 * a)).tobytes()
+    # reductions: tree order, toleranced against the oracle's sequential fold
+    oa, ob = o.SpVector.mkSpVR(n, a), o.SpVector.mkSpVR(n, b)
+    s = np.abs(a * b).sum()
+    assert abs(va.dot(vb) - oa.dot(ob)) <= 64 * U * s + 1e-300
+    assert abs(va.norm2Sq() - oa.norm2Sq()) <= 64 * U * (a * a).sum()
+    assert abs(va.norm2() - oa.norm2()) <= 64 * U * oa.norm2()
+    nv = va.normalize2().toDenseListSV()
+    np.testing.assert_allclose(nv, oa.normalize2().toDenseListSV(), rtol=1e-14, atol=0)
+    # deterministic: same bits on a second evaluation
+    assert va.dot(vb) == va.dot(vb)
+
+
+def _laplace_system(sla, o, g, seed):
+    n = g * g
+    A = sla.SpMatrix.generate(sla.GEN_LAPLACE2D, n, 5, 0, g)
+    Ao = o.SpMatrix.synth(o.GEN_LAPLACE2D, n, 5, 0, g)
+    xt = o.SpVector.synth(seed, n)
+    bo = Ao.matVec(xt)
+    b = sla.SpVector.mkSpVR(n, bo.toDenseListSV())
+    return n, A, Ao, b, bo
+
+
+@pytest.mark.parametrize("solver", ["bicgstab", "cgs", "cgne"])
+def test_krylov_trajectory_laplace(sla, o, solver):
+    """cfg 3 at reduced size (64^2 Laplacian): first 5 iterates within 1e-10 relative of the oracle."""
+    n, A, Ao, b, bo = _laplace_system(sla, o, 64, 11)
+    x0, x0o = sla.SpVector.zeroSV(n), o.SpVector.mkSpVR(n, np.zeros(n))
+    if solver == "bicgstab":
+        st, sto = sla.bicgsInit(A, b, x0), o.bicgsInit(Ao, bo, x0o)
+    elif solver == "cgs":
+        st, sto = sla.cgsInit(A, b, x0), o.cgsInit(Ao, bo, x0o)
+    else:
+        st, sto = sla.cgneInit(A, b, x0), o.cgneInit(Ao, bo, x0o)
+    rhat, rhato = st.r.copy(), bo - Ao.matVec(x0o)
+    assert st.r.toDenseListSV().tobytes() == sto.r.toDenseListSV().tobytes()
+    for it in range(5):
+        if solver == "bicgstab":
+            sla.bicgstabStep(A, rhat, st); sto = o.bicgstabStep(Ao, rhato, sto)
+        elif solver == "cgs":
+            sla.cgsStep(A, rhat, st); sto = o.cgsStep(Ao, rhato, sto)
+        else:
+            sla.cgneStep(A, st); sto = o.cgneStep(Ao, sto)
+        for f in ("x", "r", "p"):
+            g_, o_ = getattr(st, f).toDenseListSV(), getattr(sto, f).toDenseListSV()
+            assert np.abs(g_ - o_).max() <= 1e-10 * np.abs(o_).max(), (solver, it, f)
+
+
+@pytest.mark.parametrize("method", ["BICGSTAB_", "CGS_", "CGNE_"])
+def test_linsolve0_cfg1(sla, o, method):
+    """BASELINE config 1: 200x200 diagonally dominant system, x0 = 0.1: same iteration count as the oracle and
+    ||x_gpu - x_oracle||_inf <= 1e-10 ||x||_inf."""
+    n, k, seed = 200, 9, 0x5EED0001
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+    Ao = o.SpMatrix.synth(o.GEN_UNIFORM, n, k, seed)
+    xt = o.SpVector.synth(seed + 1, n)
+    bo = Ao.matVec(xt)
+    b = sla.SpVector.mkSpVR(n, bo.toDenseListSV())
+    x, it, res = sla.linSolve0(getattr(sla, method), A, b, sla.SpVector.constv(n, 0.1), info=True)
+    xo, ito, hist = o.linSolve0(getattr(o, method), Ao, bo, o.SpVector.mkSpVR(n, [0.1] * n), info=True)
+    assert it == ito
+    xg, xr = x.toDenseListSV(), xo.toDenseListSV()
+    assert np.abs(xg - xr).max() <= 1e-10 * np.abs(xr).max()
+    assert abs(res - hist[-1]) <= 1e-8 * max(hist[-1], 1e-30) + 1e-16
+    # host-buffer entry point gives the same answer
+    xh = sla.linSolve0Host(getattr(sla, method), A, bo.toDenseListSV(), np.full(n, 0.1))
+    assert xh.tobytes() == xg.tobytes()
+
+
+def test_linsolve0_nan_runs_to_cap(sla):
+    """No breakdown guards: a zero denominator yields NaN; NaN <= tol is False, so the loop runs
+    max_iters and returns silently with SLA_OK."""
+    aa = sla.SpMatrix.fromListSM((2, 2), [(0, 1, 1.0), (1, 0, -1.0)])        # r0hat . A r0hat = 0
+    b = sla.SpVector.mkSpVR(2, [1.0, 1.0])
+    x, it, res = sla.linSolve0(sla.BICGSTAB_, aa, b, sla.SpVector.zeroSV(2), nits=7, info=True)
+    assert it == 7 and np.isnan(x.toDenseListSV()).all()
+
+
+def test_arnoldi_cfg4_small(sla, o):
+    """cfg 4 at reduced size: || A Q_k - Q_{k+1} H ||_F / ||A||_F <= 1e-12 sqrt(n), Q orthonormal, H vs oracle."""
+    n, k, seed, kn = 2000, 16, 0x5EED0004, 30
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+    Ao = o.SpMatrix.synth(o.GEN_UNIFORM, n, k, seed)
+    b = sla.SpVector.generate(n, seed + 1)
+    Qd, H, brk = sla.arnoldi(A, b, kn)
+    assert not brk and H.shape == (kn + 1, kn) and Qd.dim == (n, kn + 1)
+    Q = Qd.toHost()
+    Ad = Ao.toDense()
+    assert np.linalg.norm(Ad @ Q[:, :-1] - Q @ H) / np.linalg.norm(Ad) <= 1e-12 * np.sqrt(n)
+    assert np.abs(Q.T @ Q - np.eye(kn + 1)).max() <= 1e-10
+    Qo, Ho = o.arnoldi(Ao, o.SpVector.synth(seed + 1, n), kn)
+    np.testing.assert_allclose(H, Ho, atol=1e-9 * np.abs(Ho).max())
+    np.testing.assert_allclose(Q, Qo, atol=1e-8)
+
+
+def test_gmres_converges(sla, o):
+    n, k, seed = 5000, 16, 0x5EED0004
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+    xt = sla.SpVector.generate(n, seed + 2)
+    b = A @ xt
+    x, it, res = sla.gmres(A, b, sla.SpVector.zeroSV(n), restart=30, tol_abs=1e-10, tol_rel=1e-12, info=True)
+    assert res <= 1e-9 * b.norm2() + 1e-10
+    assert ((A @ x) - b).norm2() <= 1e-9 * b.norm2() + 1e-10
+    np.testing.assert_allclose(x.toDenseListSV(), xt.toDenseListSV(), atol=1e-8)
+
+
+# =============================================================== BASELINE sizes, size-independent properties
+
+def _seq_row_dot(cols, vals, x):
+    acc = 0.0
+    for c, v in zip(cols.tolist(), vals.tolist()):
+        acc = acc + v * x[c]
+    return acc
+
+
+@pytest.mark.parametrize("kind,band", [("uniform", 0), ("banded", 65536)])
+def test_full_size_spmv_cfg2(sla, o, kind, band):
+    """BASELINE config 2 (10M x 10M, 32 nnz/row): sampled rows regenerated by the oracle are bit-exact; linearity."""
+    n, k, seed = 10_000_000, 32, 0x5EED0002
+    gk = sla.GEN_UNIFORM if kind == "uniform" else sla.GEN_BANDED
+    A = sla.SpMatrix.generate(gk, n, k, seed, band)
+    assert A.nnz == n * k
+    x = sla.SpVector.generate(n, seed + 1)
+    y = (A @ x).toDenseListSV()
+    xh = x.toDenseListSV()
+    rng = np.random.default_rng(5)
+    rows = np.concatenate([[0, 1, n - 1, n - 2, 63, 64, 65], rng.integers(0, n, 300)])
+    for r in rows.tolist():
+        cols, vals = o.synth_row(gk, n, k, seed, band, r)
+        assert y[r] == _seq_row_dot(cols, vals, xh), r
+    # linearity: A(2x) == 2 A x exactly (power-of-two scaling commutes with rounding)
+    y2 = (A @ (2.0 * x)).toDenseListSV()
+    assert y2.tobytes() == (2.0 * y).tobytes()
+    # dot fused epilogue vs separate dot: one BiCGSTAB step keeps going without NaN
+    assert np.isfinite(y).all()
+
+
+def test_full_size_bicgstab_cfg3(sla, o):
+    """BASELINE config 3 (5-point Laplacian 4096^2): A*1 is the boundary indicator; residual of b = A x_true drops."""
+    g = 4096
+    n = g * g
+    A = sla.SpMatrix.generate(sla.GEN_LAPLACE2D, n, 5, 0, g)
+    assert A.nnz == 5 * n - 4 * g
+    y = (A @ sla.SpVector.onesSV(n)).toDenseListSV().reshape(g, g)
+    exp = np.zeros((g, g))
+    exp[0, :] += 1; exp[-1, :] += 1; exp[:, 0] += 1; exp[:, -1] += 1
+    assert np.array_equal(y, exp)
+    xt = sla.SpVector.generate(n, 3)
+    b = A @ xt
+    x0 = sla.SpVector.zeroSV(n)
+    st = sla.bicgsInit(A, b, x0)
+    rhat = st.r.copy()
+    r0 = st.r.norm2()
+    for _ in range(20):
+        sla.bicgstabStep(A, rhat, st)
+    # recurrence residual equals the true residual to rounding, and has decreased
+    true_res = ((A @ st.x) - b).norm2()
+    assert abs(true_res - st.r.norm2()) <= 1e-8 * r0
+    assert true_res < 0.5 * r0
