@@ -2,6 +2,7 @@
 #include "blas1.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 
 #define SLA_VERSION_STR "sla-b200 0.1 (sm_100a)"
@@ -31,6 +32,8 @@ static sla_status ctx_create(int device, int rank, int world, sla_ctx** out) {
   if (!c) return SLA_ERR_ALLOC;
   memset(c, 0, sizeof(*c));
   c->device = device; c->rank = rank; c->world = world;
+  c->spmv_hints = 3;
+  if (const char* h = getenv("SLA_SPMV_HINTS")) c->spmv_hints = atoi(h);
   SLA_CUDA(c, cudaSetDevice(device));
   SLA_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   SLA_CUDA(c, cudaEventCreate(&c->ev0));
@@ -66,7 +69,7 @@ extern "C" void sla_finalize(sla_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->nccl) sla_dist_detach(c);
-  sla_vec_free(c->scratch_x); sla_vec_free(c->scratch_y);
+  sla_vec_free(c->scratch_x); sla_vec_free(c->scratch_y); sla_vec_free(c->scratch_r);
   cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->counter); cudaFreeHost(c->h_scal);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);

@@ -9,14 +9,15 @@
 #include "../../include/sla_b200.h"
 
 #define SLA_NUM_SMS 148          // B200: 148 SMs (2 dies x 74)
-#define SLA_SCAL_SLOTS 512       // device scalar slots per ctx
+#define SLA_SCAL_SLOTS 1024      // device scalar slots per ctx
 #define SLA_MAX_KRYLOV 384       // max Arnoldi / GMRES basis size (H column lives in scal[S_HCOL..])
 #define SLA_MAX_PARTIALS (1 << 20)
 
 // device scalar slots (doubles living in ctx->scal)
 enum {
   S_RHO = 0, S_D1, S_ALPHA, S_D3, S_D4, S_OMEGA, S_D5, S_BETA, S_RES2, S_TMP0, S_TMP1, S_TMP2, S_NRM,
-  S_RR, S_PP, S_RHO_NEW, S_INVN, S_HCOL = 64 /* .. S_HCOL + SLA_MAX_KRYLOV + 1 : one Hessenberg column */
+  S_RR, S_PP, S_RHO_NEW, S_INVN, S_HCOL = 64 /* .. + SLA_MAX_KRYLOV + 1 : one Hessenberg column */,
+  S_HCOL2 = 512 /* .. + SLA_MAX_KRYLOV + 1 : re-orthogonalisation correction (GMRES) */
 };
 
 struct sla_ctx {
@@ -31,6 +32,8 @@ struct sla_ctx {
   int64_t launches;
   void* nccl;                // ncclComm_t when world > 1
   struct sla_vec *scratch_x, *scratch_y;   // device staging for the host-pointer entry points
+  struct sla_vec* scratch_r;               // partial row sums of the panelised residual-norm SpMV
+  int spmv_hints;            // bit0: matrix stream L2 evict_first, bit1: x gathers L2 evict_last (env SLA_SPMV_HINTS)
   const void* scal_owner;    // Krylov state whose recurrence scalars currently live in scal[]
   char err[512];
 };
@@ -43,6 +46,12 @@ struct sla_vec {
   bool owns;
 };
 
+// one column panel of a matrix: a CSR over all rows holding only the columns of the panel (spmv.cu)
+struct sla_panel {
+  int32_t* row_ptr; int32_t* col; double* val; int32_t* tile_row;
+  int ntiles; int64_t nnz;
+};
+
 struct sla_csr {
   sla_ctx* ctx;
   int64_t m, n, nnz;
@@ -53,6 +62,8 @@ struct sla_csr {
   int ntiles;
   sla_csr* T;                // cached transpose for (<#) / CGNE
   int is_diag;               // -1 unknown, 0 / 1
+  int npanels;               // >= 2 when the column-panel copy exists
+  sla_panel* panels;         // host array of device pointers
 };
 
 struct sla_dense {
@@ -214,6 +225,7 @@ __device__ __forceinline__ void grid_reduce_finish(double (&mine)[NV], double* p
 sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi,
                            const double* u0, const double* u1, int fin, int dst);
 sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A);
+void sla_csr_free_panels(sla_csr* A);
 sla_status sla_csr_alloc(sla_ctx* c, int64_t m, int64_t n, int64_t nnz, sla_csr** out);
 sla_status sla_vec_alloc(sla_ctx* c, int64_t n, sla_vec** out);
 sla_status sla_read_scalars(sla_ctx* c, int first, int count, double* host_out);

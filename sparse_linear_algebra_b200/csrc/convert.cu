@@ -46,6 +46,7 @@ extern "C" void sla_csr_free(sla_csr* A) {
   if (!A) return;
   if (A->ctx) cudaStreamSynchronize(A->ctx->stream);
   if (A->T) sla_csr_free(A->T);
+  sla_csr_free_panels(A);
   cudaFree(A->row_ptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->tile_row);
   delete A;
 }

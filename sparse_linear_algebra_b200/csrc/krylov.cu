@@ -317,7 +317,7 @@ extern "C" sla_status sla_linsolve0_host(sla_ctx* c, int method, const sla_csr* 
 // h[k0 + k] = q_{k0+k} <.> w   for k < nc <= TS_CH        (hhcoli = fmap (`dot` aqi) qv, Sparse.hs:655)
 __global__ void __launch_bounds__(EW_THREADS)
 tsmv_t_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int k0, int nc, const double* __restrict__ w,
-              double* scal, double* partials, unsigned int* counter) {
+              double* scal, double* partials, unsigned int* counter, int slot0) {
   __shared__ double red[TS_CH * 32];
   double acc[TS_CH];
 #pragma unroll
@@ -338,7 +338,7 @@ tsmv_t_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int k0, int n
     for (int k = 0; k < nc; ++k) acc[k] += Q[(int64_t)(k0 + k) * ld + n - 1] * w[n - 1];
   }
   block_sum<TS_CH>(acc, red);
-  grid_reduce_finish<TS_CH>(acc, partials, counter, scal, FIN_STORE, S_HCOL + k0, red);
+  grid_reduce_finish<TS_CH>(acc, partials, counter, scal, FIN_STORE, slot0 + k0, red);
 }
 
 // out_i = base_i -/+ (((c_0 q_0i) + c_1 q_1i) + ... + c_{nc-1} q_{nc-1,i}), coefficients in scal[S_HCOL..];
@@ -347,10 +347,10 @@ tsmv_t_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int k0, int n
 template <int SIGN>
 __global__ void __launch_bounds__(EW_THREADS)
 lincomb_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int nc, const double* base, double* out,
-               double* scal, double* partials, unsigned int* counter, int fin) {
+               double* scal, double* partials, unsigned int* counter, int fin, int slot0) {
   __shared__ double coef[SLA_MAX_KRYLOV + 2];
   __shared__ double red[32];
-  for (int k = threadIdx.x; k < nc; k += blockDim.x) coef[k] = scal[S_HCOL + k];
+  for (int k = threadIdx.x; k < nc; k += blockDim.x) coef[k] = scal[slot0 + k];
   __syncthreads();
   double acc[1] = {0.0};
   const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -408,25 +408,31 @@ static sla_status dense_alloc(sla_ctx* c, int64_t rows, int64_t cols, sla_dense*
 
 // One Arnoldi step on the device: given basis columns 0..j of Q, append column j+1 and produce column j of H.
 //   aqi = aa #> q_j ; h_k = q_k <.> aqi (k <= j) ; w = aqi - sum_k h_k q_k ; h_{j+1} = norm2 w ; q_{j+1} = w ./ h_{j+1}
-// hcol (host, j + 2 doubles) receives the column.
-static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j, double* w, double* hcol) {
+// hcol (host, j + 2 doubles) receives the column.  reorth = false is the reference's single classical
+// Gram-Schmidt pass (Sparse.hs:655-659); reorth = true repeats the projection once (CGS2) — used by GMRES only,
+// because single-pass CGS loses orthogonality on clustered spectra.
+static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j, double* w, double* hcol, bool reorth) {
   const int64_t n = Q->rows, ld = Q->ld;
   SLA_TRY(sla_spmv_launch(c, A, Q->d + (int64_t)j * ld, w, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
   const int nq = j + 1;
-  for (int k0 = 0; k0 < nq; k0 += TS_CH) {
-    const int nc = nq - k0 < TS_CH ? nq - k0 : TS_CH;
-    tsmv_t_kernel<<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter);
+  for (int pass = 0; pass < (reorth ? 2 : 1); ++pass) {
+    const int slot0 = pass == 0 ? S_HCOL : S_HCOL2;
+    for (int k0 = 0; k0 < nq; k0 += TS_CH) {
+      const int nc = nq - k0 < TS_CH ? nq - k0 : TS_CH;
+      tsmv_t_kernel<<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, slot0);
+      SLA_LAUNCH_CHECK(c);
+    }
+    lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, FIN_NORM_INV, slot0);
     SLA_LAUNCH_CHECK(c);
   }
-  lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, FIN_NORM_INV);
-  SLA_LAUNCH_CHECK(c);
   // q_{j+1} = (recip h_{j+1,j}) .* w
   { Ptrs<1> in{{w}}; Ptrs<1> o{{Q->d + (int64_t)(j + 1) * ld}}; OpScaleDev op; op.slot = S_INVN; op.a = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
-  // read back the column: h_0..h_j from S_HCOL.., h_{j+1} = S_NRM
+  // read back the column: h_0..h_j from S_HCOL.. (+ the correction from S_HCOL2..), h_{j+1} = S_NRM
   SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + S_HCOL, c->scal + S_HCOL, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
+  if (reorth) SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + S_HCOL2, c->scal + S_HCOL2, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
   SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + S_NRM, c->scal + S_NRM, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < nq; ++k) hcol[k] = c->h_scal[S_HCOL + k];
+  for (int k = 0; k < nq; ++k) hcol[k] = c->h_scal[S_HCOL + k] + (reorth ? c->h_scal[S_HCOL2 + k] : 0.0);
   hcol[nq] = c->h_scal[S_NRM];
   return SLA_OK;
 }
@@ -461,7 +467,7 @@ extern "C" sla_status sla_arnoldi(sla_ctx* c, const sla_csr* A, const sla_vec* b
   bool brk = false;
   double hcol[SLA_MAX_KRYLOV + 2];
   while (s == SLA_OK) {
-    s = arnoldi_step(c, A, Q, i, w->d, hcol);
+    s = arnoldi_step(c, A, Q, i, w->d, hcol, false);
     if (s != SLA_OK) break;
     for (int k = 0; k <= i + 1; ++k) h_host[(int64_t)i * (kn + 1) + k] = hcol[k];
     brk = i > 0 && fabs(hcol[i + 1]) <= 1e-12;      // nearZero qipnorm (arnInit itself has no breakdown test)   :666
@@ -525,7 +531,7 @@ extern "C" sla_status sla_gmres(sla_ctx* c, const sla_csr* A, const sla_vec* b, 
     g[0] = beta;
     int j = 0;
     for (; j < m && total < o.max_iters; ++j) {
-      s = arnoldi_step(c, A, Q, j, w->d, hcol);
+      s = arnoldi_step(c, A, Q, j, w->d, hcol, true);
       if (s != SLA_OK) break;
       ++total;
       for (int k = 0; k < j; ++k) {                        // apply the previous rotations to the new column
@@ -551,7 +557,7 @@ extern "C" sla_status sla_gmres(sla_ctx* c, const sla_csr* A, const sla_vec* b, 
     if (j > 0) {
       for (int k = 0; k < j; ++k) c->h_scal[S_HCOL + k] = y[k];
       cudaMemcpyAsync(c->scal + S_HCOL, c->h_scal + S_HCOL, sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, c->stream);
-      lincomb_kernel<1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, Q->ld, n, j, x->d, x->d, c->scal, c->partials, c->counter, FIN_STORE);
+      lincomb_kernel<1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, Q->ld, n, j, x->d, x->d, c->scal, c->partials, c->counter, FIN_STORE, S_HCOL);
       c->launches++;
       if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
         s = sla_fail(c, SLA_ERR_CUDA, "gmres: CUDA error in the solution update");

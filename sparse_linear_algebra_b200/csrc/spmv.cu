@@ -6,7 +6,7 @@
 // sla_csr_build_plan).  A CTA
 //   1. streams its tile with 128-bit loads (int4 of col_idx, 2 x double2 of val; L1 no-allocate, L2
 //      evict-first so the matrix stream does not push x out of L2), gathers x[col] through the read-only
-//      path and writes the products a_ij * x_j (__dmul_rn, no FMA) into shared memory,
+//      path (L2 evict-last) and writes the products a_ij * x_j (__dmul_rn, no FMA) into shared memory,
 //   2. sums each owned row from shared memory IN ASCENDING COLUMN ORDER with __dadd_rn from a 0.0 seed —
 //      the reference's strict left fold — so rows of up to SLA_LONG_ROW entries are bit-identical to
 //      the Haskell result; longer rows are summed by one warp (lane-strided partials + shuffle tree).
@@ -15,11 +15,24 @@
 //      epilogues), reduced over the grid deterministically by the last CTA to finish.
 // The shared-memory product buffer is skewed by 2 doubles per 32 so that the per-row sequential reads of
 // equal-length rows do not pile onto one bank while the 16-byte product stores stay aligned.
+//
+// Column panels.  When x is larger than the L2 can keep resident (measured on B200: the gather rate
+// collapses once 8 n > ~48 MB, profiles/r01_l2_sweep.md) and the matrix has no column locality, the plan
+// stores a second copy of the matrix split into column panels of <= SLA_PANEL_BYTES of x each (each panel is
+// itself a CSR matrix over all rows).  (#>) then runs the same kernel once per panel in ascending column
+// order, the later passes continuing the row sums from y (ACC = true) — still the same left fold, so the
+// result stays bit-identical — while every pass gathers from an L2-resident slice of x.
 #include "common.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <stdlib.h>
 
 #define SLA_LONG_ROW 256
 #define SLA_LONG_CAP 16
 #define SPMV_THREADS 256
+#define SLA_PANEL_BYTES (40u << 20)     // x bytes per column panel
+#define SLA_PANEL_MIN_X (56u << 20)     // panelise only when 8 n exceeds this ...
+#define SLA_PANEL_MIN_SPAN (24u << 20)  // ... and an average tile touches a wider stretch of x than this
 
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
@@ -29,6 +42,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ int4 ld_stream_int4(const int* p, uint64_t pol) {
@@ -52,8 +70,8 @@ __device__ __forceinline__ double ld_keep_double(const double* p, uint64_t pol) 
 __device__ __forceinline__ int skew(int k) { return k + 2 * (k >> 5); }
 
 template <int EPI>
-__device__ __forceinline__ void row_epilogue(int r, double acc, double* __restrict__ y,
-                                             const double* __restrict__ u0, double& e0, double& e1) {
+__device__ __forceinline__ void row_epilogue(int r, double acc, double* y, const double* __restrict__ u0,
+                                             double& e0, double& e1) {
   if (EPI == EPI_RESNORM) {
     double d = __dsub_rn(acc, u0[r]);          // (aa #> x) ^-^ b, then (**2)   Sparse.hs:1041
     e0 += d * d;
@@ -64,12 +82,13 @@ __device__ __forceinline__ void row_epilogue(int r, double acc, double* __restri
   if (EPI == EPI_DOT2_YY) e1 += acc * acc;
 }
 
-template <int TILE, int EPI>
+// ACC = false: row sums start from 0.0.  ACC = true: they continue from yin[r] (a later column panel).
+template <int TILE, int EPI, bool ACC>
 __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val,
-                 const double* __restrict__ x, double* __restrict__ y, const int* __restrict__ tile_row,
+                 const double* __restrict__ x, const double* yin, double* y, const int* __restrict__ tile_row,
                  const double* __restrict__ u0, double* partials, unsigned int* counter, double* scal,
-                 int fin, int dst) {
+                 int fin, int dst, int hints) {
   constexpr int PER = TILE / (SPMV_THREADS * 4);          // 128-bit column groups per thread
   __shared__ __align__(16) double prod[TILE + 2 * (TILE / 32)];
   __shared__ double red[2 * 32];
@@ -85,8 +104,8 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
 
   // ---- phase 1: stream the tile, gather x, write products --------------------------------------
   if (nrows > 0) {
-    const uint64_t pol_stream = policy_evict_first();
-    const uint64_t pol_keep = policy_evict_last();
+    const uint64_t pol_stream = (hints & 1) ? policy_evict_first() : policy_evict_normal();
+    const uint64_t pol_keep = (hints & 2) ? policy_evict_last() : policy_evict_normal();
     int4 c[PER];
     double2 v[PER][2];
 #pragma unroll
@@ -131,7 +150,7 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
     }
     const int ks = s - base, ke = e - base;
     const int kin = ke < TILE ? ke : TILE;
-    double acc = 0.0;                                        // sum = strict left fold from 0
+    double acc = ACC ? yin[r] : 0.0;                         // sum = strict left fold from 0
     for (int k = ks; k < kin; ++k) acc = __dadd_rn(acc, prod[skew(k)]);
     for (int k = (ks > TILE ? ks : TILE); k < ke; ++k) {     // tail beyond the tile (last owned row only)
       const int g = base + k;
@@ -156,7 +175,10 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
         acc += t;
       }
       acc = warp_sum(acc);
-      if (lane == 0) row_epilogue<EPI>(r, acc, y, u0, e0, e1);
+      if (lane == 0) {
+        if (ACC) acc = __dadd_rn(yin[r], acc);
+        row_epilogue<EPI>(r, acc, y, u0, e0, e1);
+      }
     }
   }
 
@@ -181,20 +203,193 @@ __global__ void spmv_plan_kernel(const int* __restrict__ row_ptr, int m, int nti
   tile_row[t] = lo;
 }
 
-sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
-  const int nt = A->ntiles;
-  if (A->tile_row == nullptr) SLA_CUDA(c, cudaMalloc(&A->tile_row, sizeof(int32_t) * (size_t)(nt + 1)));
-  spmv_plan_kernel<<<(nt + 1 + 255) / 256, 256, 0, c->stream>>>(A->row_ptr, (int)A->m, nt, SLA_SPMV_TILE, A->tile_row);
+// mean over tiles of (max col - min col): how wide a stretch of x one CTA gathers from
+__global__ void tile_span_kernel(const int* __restrict__ col, int64_t nnz, int tile, unsigned long long* __restrict__ span_sum) {
+  __shared__ int smin[32], smax[32];
+  const int64_t base = (int64_t)blockIdx.x * tile;
+  int mn = 0x7fffffff, mx = -1;
+  for (int k = threadIdx.x; k < tile && base + k < nnz; k += blockDim.x) {
+    const int cidx = col[base + k];
+    mn = min(mn, cidx); mx = max(mx, cidx);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = min(mn, smin[w]); mx = max(mx, smax[w]); }
+    if (mx >= mn) atomicAdd(span_sum, (unsigned long long)(mx - mn));
+  }
+}
+
+// start[p * m + r] = absolute offset of the first entry of row r with col >= p * width   (p = 0 .. P)
+// len  [p * m + r] = entries of row r that fall in panel p
+__global__ void panel_split_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int m, int P, int width,
+                                   int* __restrict__ start, int* __restrict__ len) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  const int s = row_ptr[r], e = row_ptr[r + 1];
+  int prev = s;
+  for (int p = 0; p < P; ++p) {
+    int nxt = e;
+    if (p + 1 < P) {
+      const long long bound = (long long)(p + 1) * width;
+      int lo = prev, hi = e;
+      while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if ((long long)col[mid] < bound) lo = mid + 1; else hi = mid;
+      }
+      nxt = lo;
+    }
+    start[(size_t)p * m + r] = prev;
+    len[(size_t)p * m + r] = nxt - prev;
+    prev = nxt;
+  }
+}
+
+// scatter every stored entry into its panel: dest = panel row_ptr[r] + (q - start[p][r])
+__global__ void panel_fill_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val,
+                                  int m, int64_t nnz, int width, const int* __restrict__ start, sla_panel* __restrict__ panels) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = m;                     // last row r with row_ptr[r] <= q
+    while (lo < hi) {
+      const int mid = lo + ((hi - lo + 1) >> 1);
+      if (row_ptr[mid] <= q) lo = mid; else hi = mid - 1;
+    }
+    const int cidx = col[q];
+    const int p = cidx / width;
+    const sla_panel pn = panels[p];
+    const int d = pn.row_ptr[lo] + (int)(q - start[(size_t)p * m + lo]);
+    pn.col[d] = cidx;
+    pn.val[d] = val[q];
+  }
+}
+
+__global__ void set_last_kernel(int32_t* row_ptr, const int32_t* len, int m) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) row_ptr[m] = m > 0 ? row_ptr[m - 1] + len[m - 1] : 0;
+}
+
+static sla_status build_tile_plan(sla_ctx* c, const int32_t* row_ptr, int64_t m, int ntiles, int32_t** tile_row) {
+  if (*tile_row == nullptr) SLA_CUDA(c, cudaMalloc(tile_row, sizeof(int32_t) * (size_t)(ntiles + 1)));
+  spmv_plan_kernel<<<(ntiles + 1 + 255) / 256, 256, 0, c->stream>>>(row_ptr, (int)m, ntiles, SLA_SPMV_TILE, *tile_row);
   SLA_LAUNCH_CHECK(c);
   return SLA_OK;
 }
 
-template <int EPI>
-static sla_status launch_epi(sla_ctx* c, const sla_csr* A, const double* x, double* y, const double* u0, int fin, int dst) {
-  spmv_tile_kernel<SLA_SPMV_TILE, EPI><<<A->ntiles, SPMV_THREADS, 0, c->stream>>>(
-      A->row_ptr, A->col, A->val, x, y, A->tile_row, u0, c->partials, c->counter, c->scal, fin, dst);
+void sla_csr_free_panels(sla_csr* A) {
+  if (!A->panels) return;
+  for (int p = 0; p < A->npanels; ++p) {
+    cudaFree(A->panels[p].row_ptr); cudaFree(A->panels[p].col); cudaFree(A->panels[p].val); cudaFree(A->panels[p].tile_row);
+  }
+  delete[] A->panels;
+  A->panels = nullptr; A->npanels = 0;
+}
+
+static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
+  const int m = (int)A->m;
+  int width = (int)((A->n + P - 1) / P);
+  width = (width + 15) & ~15;
+  P = (int)((A->n + width - 1) / width);
+  if (P < 2) return SLA_OK;
+  int *start = nullptr, *len = nullptr;
+  sla_panel* d_panels = nullptr;
+  void* tmp = nullptr;
+  A->panels = new sla_panel[P]();
+  A->npanels = P;
+  sla_status s = SLA_OK;
+  do {
+    if (cudaMalloc(&start, sizeof(int) * (size_t)P * m) != cudaSuccess || cudaMalloc(&len, sizeof(int) * (size_t)P * m) != cudaSuccess ||
+        cudaMalloc(&d_panels, sizeof(sla_panel) * P) != cudaSuccess) { s = sla_fail(c, SLA_ERR_ALLOC, "spmv plan: cudaMalloc failed"); break; }
+    panel_split_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(A->row_ptr, A->col, m, P, width, start, len);
+    c->launches++;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, len, len, m, c->stream);
+    if (cudaMalloc(&tmp, tb ? tb : 1) != cudaSuccess) { s = sla_fail(c, SLA_ERR_ALLOC, "spmv plan: cudaMalloc failed"); break; }
+    for (int p = 0; p < P && s == SLA_OK; ++p) {
+      sla_panel& pn = A->panels[p];
+      if (cudaMalloc(&pn.row_ptr, sizeof(int32_t) * (size_t)(m + 1)) != cudaSuccess) { s = sla_fail(c, SLA_ERR_ALLOC, "spmv plan: cudaMalloc failed"); break; }
+      cub::DeviceScan::ExclusiveSum(tmp, tb, len + (size_t)p * m, pn.row_ptr, m, c->stream);
+      set_last_kernel<<<1, 32, 0, c->stream>>>(pn.row_ptr, len + (size_t)p * m, m);
+      c->launches += 3;
+      int32_t nz = 0;
+      cudaMemcpyAsync(&nz, pn.row_ptr + m, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) { s = sla_fail(c, SLA_ERR_CUDA, "spmv plan: CUDA error"); break; }
+      pn.nnz = nz;
+      pn.ntiles = nz / SLA_SPMV_TILE + 1;
+      const size_t pn_pad = (size_t)pn.ntiles * SLA_SPMV_TILE;
+      if (cudaMalloc(&pn.col, sizeof(int32_t) * pn_pad) != cudaSuccess || cudaMalloc(&pn.val, sizeof(double) * pn_pad) != cudaSuccess) {
+        s = sla_fail(c, SLA_ERR_ALLOC, "spmv plan: cudaMalloc failed for a column panel"); break;
+      }
+      cudaMemsetAsync(pn.col + nz, 0, sizeof(int32_t) * (pn_pad - nz), c->stream);
+      cudaMemsetAsync(pn.val + nz, 0, sizeof(double) * (pn_pad - nz), c->stream);
+      s = build_tile_plan(c, pn.row_ptr, m, pn.ntiles, &pn.tile_row);
+    }
+    if (s != SLA_OK) break;
+    cudaMemcpyAsync(d_panels, A->panels, sizeof(sla_panel) * P, cudaMemcpyHostToDevice, c->stream);
+    if (A->nnz > 0) {
+      int64_t blocks = (A->nnz + 255) / 256;
+      if (blocks > SLA_NUM_SMS * 32) blocks = SLA_NUM_SMS * 32;
+      panel_fill_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(A->row_ptr, A->col, A->val, m, A->nnz, width, start, d_panels);
+      c->launches++;
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) s = sla_fail(c, SLA_ERR_CUDA, "spmv plan: CUDA error while building column panels");
+  } while (0);
+  cudaFree(start); cudaFree(len); cudaFree(d_panels); cudaFree(tmp);
+  if (s != SLA_OK) { cudaGetLastError(); sla_csr_free_panels(A); }
+  return s;
+}
+
+// Builds the tile plan and, when x cannot stay L2-resident and the matrix has no column locality, the
+// column-panel copy.  SLA_SPMV_PANELS=1 disables panels, =P (>1) forces P panels, unset/0 = automatic.
+sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
+  SLA_TRY(build_tile_plan(c, A->row_ptr, A->m, A->ntiles, &A->tile_row));
+  sla_csr_free_panels(A);
+  int want = 0;
+  if (const char* e = getenv("SLA_SPMV_PANELS")) want = atoi(e);
+  if (want == 1 || A->nnz == 0 || A->m == 0) return SLA_OK;
+  if (want == 0) {
+    if ((uint64_t)A->n * 8u <= SLA_PANEL_MIN_X) return SLA_OK;
+    unsigned long long* d_span = nullptr;
+    unsigned long long h_span = 0;
+    SLA_CUDA(c, cudaMalloc(&d_span, sizeof(unsigned long long)));
+    cudaMemsetAsync(d_span, 0, sizeof(unsigned long long), c->stream);
+    const int nt = (int)((A->nnz + SLA_SPMV_TILE - 1) / SLA_SPMV_TILE);
+    tile_span_kernel<<<nt, 256, 0, c->stream>>>(A->col, A->nnz, SLA_SPMV_TILE, d_span);
+    c->launches++;
+    cudaMemcpyAsync(&h_span, d_span, sizeof(h_span), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_span);
+    SLA_CUDA(c, e);
+    const double mean_span_bytes = 8.0 * (double)h_span / (double)nt;
+    if (mean_span_bytes <= (double)SLA_PANEL_MIN_SPAN) return SLA_OK;
+    want = (int)(((uint64_t)A->n * 8u + SLA_PANEL_BYTES - 1) / SLA_PANEL_BYTES);
+  }
+  if (want > 64) want = 64;
+  return build_panels(c, A, want);
+}
+
+template <int EPI, bool ACC>
+static sla_status launch_one(sla_ctx* c, const int32_t* row_ptr, const int32_t* col, const double* val, const int32_t* tile_row,
+                             int ntiles, const double* x, const double* yin, double* y, const double* u0, int fin, int dst) {
+  spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC><<<ntiles, SPMV_THREADS, 0, c->stream>>>(
+      row_ptr, col, val, x, yin, y, tile_row, u0, c->partials, c->counter, c->scal, fin, dst, c->spmv_hints);
   SLA_LAUNCH_CHECK(c);
   return SLA_OK;
+}
+
+template <bool ACC>
+static sla_status launch_epi(sla_ctx* c, int epi, const int32_t* row_ptr, const int32_t* col, const double* val,
+                             const int32_t* tile_row, int ntiles, const double* x, const double* yin, double* y,
+                             const double* u0, int fin, int dst) {
+  switch (epi) {
+    case EPI_NONE:    return launch_one<EPI_NONE, ACC>(c, row_ptr, col, val, tile_row, ntiles, x, yin, y, u0, fin, dst);
+    case EPI_DOT1:    return launch_one<EPI_DOT1, ACC>(c, row_ptr, col, val, tile_row, ntiles, x, yin, y, u0, fin, dst);
+    case EPI_DOT2_YY: return launch_one<EPI_DOT2_YY, ACC>(c, row_ptr, col, val, tile_row, ntiles, x, yin, y, u0, fin, dst);
+    case EPI_RESNORM: return launch_one<EPI_RESNORM, ACC>(c, row_ptr, col, val, tile_row, ntiles, x, yin, y, u0, fin, dst);
+  }
+  return sla_fail(c, SLA_ERR_INVALID, "spmv: unknown epilogue");
 }
 
 // y = A x with an optional fused epilogue.  u1 is reserved (EPI_DOT2_YY uses y itself).
@@ -203,11 +398,23 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   (void)u1;
   if (A->ntiles > SLA_MAX_PARTIALS) return sla_fail(c, SLA_ERR_INVALID, "spmv: matrix has too many tiles");
   if (A->m == 0) return SLA_OK;
-  switch (epi) {
-    case EPI_NONE:    return launch_epi<EPI_NONE>(c, A, x, y, u0, fin, dst);
-    case EPI_DOT1:    return launch_epi<EPI_DOT1>(c, A, x, y, u0, fin, dst);
-    case EPI_DOT2_YY: return launch_epi<EPI_DOT2_YY>(c, A, x, y, u0, fin, dst);
-    case EPI_RESNORM: return launch_epi<EPI_RESNORM>(c, A, x, y, u0, fin, dst);
+  if (A->npanels < 2)
+    return launch_epi<false>(c, epi, A->row_ptr, A->col, A->val, A->tile_row, A->ntiles, x, nullptr, y, u0, fin, dst);
+  // column panels in ascending order; the epilogue rides on the last pass
+  double* ybuf = y;
+  if (epi == EPI_RESNORM) {          // y is not an output of this mode: keep the partial sums in a scratch vector
+    if (!c->scratch_r || c->scratch_r->n != A->m) {
+      sla_vec_free(c->scratch_r); c->scratch_r = nullptr;
+      SLA_TRY(sla_vec_alloc(c, A->m, &c->scratch_r));
+    }
+    ybuf = c->scratch_r->d;
   }
-  return sla_fail(c, SLA_ERR_INVALID, "spmv: unknown epilogue");
+  for (int p = 0; p < A->npanels; ++p) {
+    const sla_panel& pn = A->panels[p];
+    const bool last = p + 1 == A->npanels;
+    const int e = last ? epi : EPI_NONE;
+    if (p == 0) SLA_TRY(launch_epi<false>(c, e, pn.row_ptr, pn.col, pn.val, pn.tile_row, pn.ntiles, x, nullptr, ybuf, u0, fin, dst));
+    else        SLA_TRY(launch_epi<true>(c, e, pn.row_ptr, pn.col, pn.val, pn.tile_row, pn.ntiles, x, ybuf, ybuf, u0, fin, dst));
+  }
+  return SLA_OK;
 }

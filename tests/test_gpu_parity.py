@@ -261,6 +261,36 @@ def test_spmv_long_rows_within_bound(sla, o):
     assert (~short).sum() == 5
 
 
+@pytest.mark.parametrize("panels", [2, 3, 7])
+def test_spmv_column_panels_bit_exact(sla, o, monkeypatch, panels):
+    """The column-panel layout (used when x outgrows L2) continues each row's left fold from panel to panel:
+    short rows stay bit-identical, long rows within the bound, and the fused Krylov epilogues still work."""
+    monkeypatch.setenv("SLA_SPMV_PANELS", str(panels))
+    rng = np.random.default_rng(30 + panels)
+    m, n = 6000, 5000
+    i, j, v = _rand_coo(rng, m, n, 50000, long_rows=[(5, 300), (4000, 2500)])
+    A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+    Ao = o.SpMatrix.fromCOO((m, n), i, j, v)
+    x = rng.standard_normal(n)
+    y = (A @ sla.SpVector.mkSpVR(n, x)).toDenseListSV()
+    yo = Ao.matVec(o.SpVector.mkSpVR(n, x)).toDenseListSV()
+    rp, ci, va = A.toCSR()
+    lens = np.diff(rp)
+    short = lens <= 256                      # every per-panel segment of such a row is summed sequentially
+    assert y[short].tobytes() == yo[short].tobytes()
+    absum = np.array([np.abs(va[rp[r]:rp[r + 1]] * x[ci[rp[r]:rp[r + 1]]]).sum() for r in range(m)])
+    assert np.all(np.abs(y - yo) <= (lens + 2) * U * absum)
+    # Krylov epilogues (fused dots, residual norm) through the panel path: cfg-1 system, same iteration count
+    nn, k, seed = 200, 9, 0x5EED0001
+    S = sla.SpMatrix.generate(sla.GEN_UNIFORM, nn, k, seed)
+    So = o.SpMatrix.synth(o.GEN_UNIFORM, nn, k, seed)
+    bo = So.matVec(o.SpVector.synth(seed + 1, nn))
+    xg, it, _ = sla.linSolve0(sla.BICGSTAB_, S, sla.SpVector.mkSpVR(nn, bo.toDenseListSV()), sla.SpVector.constv(nn, 0.1), info=True)
+    xo, ito, _ = o.linSolve0(o.BICGSTAB_, So, bo, o.SpVector.mkSpVR(nn, [0.1] * nn), info=True)
+    assert it == ito
+    assert np.abs(xg.toDenseListSV() - xo.toDenseListSV()).max() <= 1e-10 * np.abs(xo.toDenseListSV()).max()
+
+
 def test_synthetic_generators_match_oracle(sla, o):
     for kind, n, k, band in ((sla.GEN_UNIFORM, 3000, 32, 0), (sla.GEN_BANDED, 3000, 16, 100),
                              (sla.GEN_LAPLACE2D, 64 * 64, 5, 64), (sla.GEN_UNIFORM, 40, 64, 0)):
@@ -286,12 +316,18 @@ def test_vector_ops(sla, o, n):
     assert vb.axpy(-1.7, va).toDenseListSV().tobytes() == (b + (-1.7 * a)).tobytes()
     # reductions: tree order, toleranced against the oracle's sequential fold
     oa, ob = o.SpVector.mkSpVR(n, a), o.SpVector.mkSpVR(n, b)
+    import math
+
     s = np.abs(a * b).sum()
-    assert abs(va.dot(vb) - oa.dot(ob)) <= 64 * U * s + 1e-300
-    assert abs(va.norm2Sq() - oa.norm2Sq()) <= 64 * U * (a * a).sum()
-    assert abs(va.norm2() - oa.norm2()) <= 64 * U * oa.norm2()
+    # hard bound against the oracle: both are n-term summations of the same products
+    assert abs(va.dot(vb) - oa.dot(ob)) <= 2 * n * U * s + 1e-300
+    assert abs(va.norm2Sq() - oa.norm2Sq()) <= 2 * n * U * (a * a).sum()
+    assert abs(va.norm2() - oa.norm2()) <= 2 * n * U * oa.norm2()
+    # tree-reduction quality against the exactly-summed products
+    assert abs(va.dot(vb) - math.fsum((a * b).tolist())) <= 64 * U * s + 1e-300
+    assert abs(va.norm2Sq() - math.fsum((a * a).tolist())) <= 64 * U * (a * a).sum()
     nv = va.normalize2().toDenseListSV()
-    np.testing.assert_allclose(nv, oa.normalize2().toDenseListSV(), rtol=1e-14, atol=0)
+    np.testing.assert_allclose(nv, oa.normalize2().toDenseListSV(), rtol=2 * n * U + 4 * U, atol=0)
     # deterministic: same bits on a second evaluation
     assert va.dot(vb) == va.dot(vb)
 
@@ -372,10 +408,18 @@ def test_arnoldi_cfg4_small(sla, o):
     Q = Qd.toHost()
     Ad = Ao.toDense()
     assert np.linalg.norm(Ad @ Q[:, :-1] - Q @ H) / np.linalg.norm(Ad) <= 1e-12 * np.sqrt(n)
-    assert np.abs(Q.T @ Q - np.eye(kn + 1)).max() <= 1e-10
     Qo, Ho = o.arnoldi(Ao, o.SpVector.synth(seed + 1, n), kn)
-    np.testing.assert_allclose(H, Ho, atol=1e-9 * np.abs(Ho).max())
-    np.testing.assert_allclose(Q, Qo, atol=1e-8)
+    # The reference orthogonalises with CLASSICAL Gram-Schmidt (Sparse.hs:655-657), which loses orthogonality
+    # on this clustered-spectrum matrix (the oracle reaches |Q^T Q - I| ~ 0.7 by column 30).  Parity therefore
+    # means: the same loss as the oracle, and agreement column by column while the basis is well conditioned.
+    for j in (6, 10):
+        eg = np.abs(Q[:, :j].T @ Q[:, :j] - np.eye(j)).max()
+        eo = np.abs(Qo[:, :j].T @ Qo[:, :j] - np.eye(j)).max()
+        assert eg <= 10 * eo + 1e-13
+    np.testing.assert_allclose(H[:, :8], Ho[:, :8], atol=1e-9 * np.abs(Ho).max())
+    np.testing.assert_allclose(Q[:, :8], Qo[:, :8], atol=1e-9)
+    eg, eo = np.abs(Q.T @ Q - np.eye(kn + 1)).max(), np.abs(Qo.T @ Qo - np.eye(kn + 1)).max()
+    assert 0.01 * eo <= eg <= 100 * eo
 
 
 def test_gmres_converges(sla, o):
