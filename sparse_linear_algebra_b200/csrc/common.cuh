@@ -49,7 +49,7 @@ struct sla_vec {
 // one column panel of a matrix: a CSR over all rows holding only the columns of the panel (spmv.cu)
 struct sla_panel {
   int32_t* row_ptr; int32_t* col; double* val; int32_t* tile_row;
-  int ntiles; int64_t nnz;
+  int ntiles; int64_t nnz; int skew_a;
 };
 
 struct sla_csr {
@@ -62,6 +62,8 @@ struct sla_csr {
   int ntiles;
   sla_csr* T;                // cached transpose for (<#) / CGNE
   int is_diag;               // -1 unknown, 0 / 1
+  int skew_a;                // shared-memory skew shift of the SpMV product buffer (spmv.cu)
+  int hints;                 // cache-hint bits of the SpMV loads chosen by the plan (spmv.cu)
   int npanels;               // >= 2 when the column-panel copy exists
   sla_panel* panels;         // host array of device pointers
 };

@@ -4,17 +4,21 @@
 // Decomposition.  The nnz stream (col_idx | val) is cut into fixed tiles of SLA_SPMV_TILE entries; tile t
 // OWNS the rows whose first entry lies inside it (tile_row[t] .. tile_row[t+1], found once per matrix by
 // sla_csr_build_plan).  A CTA
-//   1. streams its tile with 128-bit loads (int4 of col_idx, 2 x double2 of val; L1 no-allocate, L2
-//      evict-first so the matrix stream does not push x out of L2), gathers x[col] through the read-only
-//      path (L2 evict-last) and writes the products a_ij * x_j (__dmul_rn, no FMA) into shared memory,
+//   1. streams its tile with fully coalesced lane-contiguous loads (each warp instruction reads 128 B of
+//      col_idx / 256 B of val; L1 no-allocate, L2 evict-first so the matrix stream does not push x out of
+//      L2), gathers x[col] through the read-only path (L2 evict-last) and writes the products a_ij * x_j
+//      (__dmul_rn, no FMA) into shared memory with conflict-free 8-byte stores,
 //   2. sums each owned row from shared memory IN ASCENDING COLUMN ORDER with __dadd_rn from a 0.0 seed —
 //      the reference's strict left fold — so rows of up to SLA_LONG_ROW entries are bit-identical to
 //      the Haskell result; longer rows are summed by one warp (lane-strided partials + shuffle tree).
 //      A row that runs past the tile end reads its tail straight from global memory.
 //   3. optionally folds the row results into up to two dot products / a residual norm (the Krylov
 //      epilogues), reduced over the grid deterministically by the last CTA to finish.
-// The shared-memory product buffer is skewed by 2 doubles per 32 so that the per-row sequential reads of
-// equal-length rows do not pile onto one bank while the 16-byte product stores stay aligned.
+// The shared-memory product buffer is skewed, loc(k) = k + (k >> a), with a chosen per matrix from the
+// typical row length L (2^a = largest power of two dividing L; no skew for odd L) so that the per-row
+// sequential reads of equal-length rows hit distinct banks: thread t reads (L + L/2^a) t + i, an odd stride.
+// (ncu, profiles/r01_*: with 16-byte stores and a fixed skew 45-60 % of the shared-memory wavefronts were
+// bank conflicts and the L1TEX data pipe, not HBM, bounded the kernel.)
 //
 // Column panels.  When x is larger than the L2 can keep resident (measured on B200: the gather rate
 // collapses once 8 n > ~48 MB, profiles/r01_l2_sweep.md) and the matrix has no column locality, the plan
@@ -33,6 +37,7 @@
 #define SLA_PANEL_BYTES (40u << 20)     // x bytes per column panel
 #define SLA_PANEL_MIN_X (56u << 20)     // panelise only when 8 n exceeds this ...
 #define SLA_PANEL_MIN_SPAN (24u << 20)  // ... and an average tile touches a wider stretch of x than this
+#define SLA_GATHER_NA_SPAN (512u << 10) // x gathers bypass L1 allocation when a tile's column span exceeds this
 
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
@@ -49,16 +54,14 @@ __device__ __forceinline__ uint64_t policy_evict_normal() {
   asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ int4 ld_stream_int4(const int* p, uint64_t pol) {
-  int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+__device__ __forceinline__ int ld_stream_int(const int* p, uint64_t pol) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
   return r;
 }
-__device__ __forceinline__ double2 ld_stream_double2(const double* p, uint64_t pol) {
-  double2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
-               : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+__device__ __forceinline__ double ld_stream_double(const double* p, uint64_t pol) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
   return r;
 }
 __device__ __forceinline__ double ld_keep_double(const double* p, uint64_t pol) {
@@ -67,7 +70,13 @@ __device__ __forceinline__ double ld_keep_double(const double* p, uint64_t pol) 
   return r;
 }
 
-__device__ __forceinline__ int skew(int k) { return k + 2 * (k >> 5); }
+__device__ __forceinline__ double ld_keep_double_na(const double* p, uint64_t pol) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+  return r;
+}
+
+__device__ __forceinline__ int skew(int k, int a) { return k + (k >> a); }   // a = 31: no skew
 
 template <int EPI>
 __device__ __forceinline__ void row_epilogue(int r, double acc, double* y, const double* __restrict__ u0,
@@ -89,8 +98,8 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
                  const double* __restrict__ x, const double* yin, double* y, const int* __restrict__ tile_row,
                  const double* __restrict__ u0, double* partials, unsigned int* counter, double* scal,
                  int fin, int dst, int hints) {
-  constexpr int PER = TILE / (SPMV_THREADS * 4);          // 128-bit column groups per thread
-  __shared__ __align__(16) double prod[TILE + 2 * (TILE / 32)];
+  constexpr int PER = TILE / SPMV_THREADS;                // entries per thread, lane-contiguous
+  __shared__ double prod[TILE + TILE / 8];              // keep CTA smem small: the L1 left over holds the in-flight gathers
   __shared__ double red[2 * 32];
   __shared__ int long_rows[SLA_LONG_CAP];
   __shared__ int n_long;
@@ -100,40 +109,29 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
   const int base = tile * TILE;
   const int row_lo = tile_row[tile], row_hi = tile_row[tile + 1];
   const int nrows = row_hi - row_lo;
+  const int sk = hints >> 8;                              // skew shift a
   if (tid == 0) n_long = 0;
 
   // ---- phase 1: stream the tile, gather x, write products --------------------------------------
   if (nrows > 0) {
     const uint64_t pol_stream = (hints & 1) ? policy_evict_first() : policy_evict_normal();
     const uint64_t pol_keep = (hints & 2) ? policy_evict_last() : policy_evict_normal();
-    int4 c[PER];
-    double2 v[PER][2];
+    int c[PER];
+    double v[PER];
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
-      const int p = (it * SPMV_THREADS + tid) * 4;
-      c[it] = ld_stream_int4(col + base + p, pol_stream);
-      v[it][0] = ld_stream_double2(val + base + p, pol_stream);
-      v[it][1] = ld_stream_double2(val + base + p + 2, pol_stream);
+      const int k = it * SPMV_THREADS + tid;
+      c[it] = ld_stream_int(col + base + k, pol_stream);
+      v[it] = ld_stream_double(val + base + k, pol_stream);
     }
-    double xv[PER][4];
+    double xv[PER];
+#pragma unroll
+    for (int it = 0; it < PER; ++it)
+      xv[it] = (hints & 4) ? ld_keep_double_na(x + c[it], pol_keep) : ld_keep_double(x + c[it], pol_keep);
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
-      xv[it][0] = ld_keep_double(x + c[it].x, pol_keep);
-      xv[it][1] = ld_keep_double(x + c[it].y, pol_keep);
-      xv[it][2] = ld_keep_double(x + c[it].z, pol_keep);
-      xv[it][3] = ld_keep_double(x + c[it].w, pol_keep);
-    }
-#pragma unroll
-    for (int it = 0; it < PER; ++it) {
-      const int p = (it * SPMV_THREADS + tid) * 4;
-      double2 p0, p1;
-      p0.x = __dmul_rn(v[it][0].x, xv[it][0]);             // dotu: a_ij * x_j, matrix entry on the left
-      p0.y = __dmul_rn(v[it][0].y, xv[it][1]);
-      p1.x = __dmul_rn(v[it][1].x, xv[it][2]);
-      p1.y = __dmul_rn(v[it][1].y, xv[it][3]);
-      double2* dstp = reinterpret_cast<double2*>(prod + skew(p));
-      dstp[0] = p0;
-      dstp[1] = p1;
+      const int k = it * SPMV_THREADS + tid;
+      prod[skew(k, sk)] = __dmul_rn(v[it], xv[it]);         // dotu: a_ij * x_j, matrix entry on the left
     }
   }
   __syncthreads();
@@ -151,7 +149,7 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
     const int ks = s - base, ke = e - base;
     const int kin = ke < TILE ? ke : TILE;
     double acc = ACC ? yin[r] : 0.0;                         // sum = strict left fold from 0
-    for (int k = ks; k < kin; ++k) acc = __dadd_rn(acc, prod[skew(k)]);
+    for (int k = ks; k < kin; ++k) acc = __dadd_rn(acc, prod[skew(k, sk)]);
     for (int k = (ks > TILE ? ks : TILE); k < ke; ++k) {     // tail beyond the tile (last owned row only)
       const int g = base + k;
       acc = __dadd_rn(acc, __dmul_rn(val[g], x[col[g]]));
@@ -170,7 +168,7 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
       double acc = 0.0;
       for (int k = ks + lane; k < ke; k += 32) {
         double t;
-        if (k < TILE) t = prod[skew(k)];
+        if (k < TILE) t = prod[skew(k, sk)];
         else { const int g = base + k; t = __dmul_rn(val[g], x[col[g]]); }
         acc += t;
       }
@@ -271,6 +269,19 @@ __global__ void set_last_kernel(int32_t* row_ptr, const int32_t* len, int m) {
   if (threadIdx.x == 0 && blockIdx.x == 0) row_ptr[m] = m > 0 ? row_ptr[m - 1] + len[m - 1] : 0;
 }
 
+// skew shift a for a typical row length L: 2^a = largest power of two dividing L (odd L: no skew),
+// clamped to a >= 3 so the skewed buffer fits TILE + TILE / 8 doubles (a larger buffer pushes the
+// shared-memory carve-out to 228 KB, leaves no L1 for outstanding gathers and costs 3x on random columns).
+static int choose_skew(int64_t nnz, int64_t m) {
+  if (m <= 0 || nnz <= 0) return 31;
+  int64_t L = (nnz + m / 2) / m;
+  if (L < 1) L = 1;
+  if (L & 1) return 31;
+  int a = 0;
+  while (((L >> a) & 1) == 0) ++a;
+  return a < 3 ? 3 : a;
+}
+
 static sla_status build_tile_plan(sla_ctx* c, const int32_t* row_ptr, int64_t m, int ntiles, int32_t** tile_row) {
   if (*tile_row == nullptr) SLA_CUDA(c, cudaMalloc(tile_row, sizeof(int32_t) * (size_t)(ntiles + 1)));
   spmv_plan_kernel<<<(ntiles + 1 + 255) / 256, 256, 0, c->stream>>>(row_ptr, (int)m, ntiles, SLA_SPMV_TILE, *tile_row);
@@ -317,6 +328,7 @@ static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
       cudaMemcpyAsync(&nz, pn.row_ptr + m, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
       if (cudaStreamSynchronize(c->stream) != cudaSuccess) { s = sla_fail(c, SLA_ERR_CUDA, "spmv plan: CUDA error"); break; }
       pn.nnz = nz;
+      pn.skew_a = choose_skew(nz, m);
       pn.ntiles = nz / SLA_SPMV_TILE + 1;
       const size_t pn_pad = (size_t)pn.ntiles * SLA_SPMV_TILE;
       if (cudaMalloc(&pn.col, sizeof(int32_t) * pn_pad) != cudaSuccess || cudaMalloc(&pn.val, sizeof(double) * pn_pad) != cudaSuccess) {
@@ -341,16 +353,20 @@ static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
   return s;
 }
 
-// Builds the tile plan and, when x cannot stay L2-resident and the matrix has no column locality, the
-// column-panel copy.  SLA_SPMV_PANELS=1 disables panels, =P (>1) forces P panels, unset/0 = automatic.
+// Builds the tile plan, picks the gather cache policy and, when x cannot stay L2-resident and the matrix has
+// no column locality, the column-panel copy.
+//   SLA_SPMV_PANELS=1 disables panels, =P (>1) forces P panels, unset/0 = automatic.
+//   SLA_SPMV_HINTS overrides the cache-hint bits (1: stream evict_first, 2: x evict_last, 4: x L1 no_allocate).
 sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
   SLA_TRY(build_tile_plan(c, A->row_ptr, A->m, A->ntiles, &A->tile_row));
+  A->skew_a = choose_skew(A->nnz, A->m);
+  if (const char* e = getenv("SLA_SPMV_SKEW")) { A->skew_a = atoi(e); if (A->skew_a < 3) A->skew_a = 3; }
   sla_csr_free_panels(A);
-  int want = 0;
-  if (const char* e = getenv("SLA_SPMV_PANELS")) want = atoi(e);
-  if (want == 1 || A->nnz == 0 || A->m == 0) return SLA_OK;
-  if (want == 0) {
-    if ((uint64_t)A->n * 8u <= SLA_PANEL_MIN_X) return SLA_OK;
+  A->hints = c->spmv_hints & 3;
+  if (A->nnz == 0 || A->m == 0) return SLA_OK;
+  // how wide a stretch of x does one CTA gather from, on average?
+  double mean_span_bytes = 0.0;
+  {
     unsigned long long* d_span = nullptr;
     unsigned long long h_span = 0;
     SLA_CUDA(c, cudaMalloc(&d_span, sizeof(unsigned long long)));
@@ -362,8 +378,17 @@ sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     cudaFree(d_span);
     SLA_CUDA(c, e);
-    const double mean_span_bytes = 8.0 * (double)h_span / (double)nt;
-    if (mean_span_bytes <= (double)SLA_PANEL_MIN_SPAN) return SLA_OK;
+    mean_span_bytes = 8.0 * (double)h_span / (double)nt;
+  }
+  // Gathers with no reuse inside an SM should not allocate in L1: the L1 lines they would occupy are what
+  // tracks outstanding misses (measured: +18 % on random columns, -3 % on the 5-point stencil).
+  if (mean_span_bytes > (double)SLA_GATHER_NA_SPAN) A->hints |= 4;
+  if (getenv("SLA_SPMV_HINTS")) A->hints = c->spmv_hints & 7;
+  int want = 0;
+  if (const char* e = getenv("SLA_SPMV_PANELS")) want = atoi(e);
+  if (want == 1) return SLA_OK;
+  if (want == 0) {
+    if ((uint64_t)A->n * 8u <= SLA_PANEL_MIN_X || mean_span_bytes <= (double)SLA_PANEL_MIN_SPAN) return SLA_OK;
     want = (int)(((uint64_t)A->n * 8u + SLA_PANEL_BYTES - 1) / SLA_PANEL_BYTES);
   }
   if (want > 64) want = 64;
@@ -372,22 +397,28 @@ sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
 
 template <int EPI, bool ACC>
 static sla_status launch_one(sla_ctx* c, const int32_t* row_ptr, const int32_t* col, const double* val, const int32_t* tile_row,
-                             int ntiles, const double* x, const double* yin, double* y, const double* u0, int fin, int dst) {
+                             int ntiles, int skew_a, int hints, const double* x, const double* yin, double* y, const double* u0, int fin, int dst) {
+  static int carve_set = 0;
+  if (!carve_set) {
+    carve_set = 1;
+    if (const char* e = getenv("SLA_SPMV_CARVEOUT"))
+      cudaFuncSetAttribute(spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+  }
   spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC><<<ntiles, SPMV_THREADS, 0, c->stream>>>(
-      row_ptr, col, val, x, yin, y, tile_row, u0, c->partials, c->counter, c->scal, fin, dst, c->spmv_hints);
+      row_ptr, col, val, x, yin, y, tile_row, u0, c->partials, c->counter, c->scal, fin, dst, (hints & 0xff) | (skew_a << 8));
   SLA_LAUNCH_CHECK(c);
   return SLA_OK;
 }
 
 template <bool ACC>
 static sla_status launch_epi(sla_ctx* c, int epi, const int32_t* row_ptr, const int32_t* col, const double* val,
-                             const int32_t* tile_row, int ntiles, const double* x, const double* yin, double* y,
+                             const int32_t* tile_row, int ntiles, int skew_a, int hints, const double* x, const double* yin, double* y,
                              const double* u0, int fin, int dst) {
   switch (epi) {
-    case EPI_NONE:    return launch_one<EPI_NONE, ACC>(c, row_ptr, col, val, tile_row, ntiles, x, yin, y, u0, fin, dst);
-    case EPI_DOT1:    return launch_one<EPI_DOT1, ACC>(c, row_ptr, col, val, tile_row, ntiles, x, yin, y, u0, fin, dst);
-    case EPI_DOT2_YY: return launch_one<EPI_DOT2_YY, ACC>(c, row_ptr, col, val, tile_row, ntiles, x, yin, y, u0, fin, dst);
-    case EPI_RESNORM: return launch_one<EPI_RESNORM, ACC>(c, row_ptr, col, val, tile_row, ntiles, x, yin, y, u0, fin, dst);
+    case EPI_NONE:    return launch_one<EPI_NONE, ACC>(c, row_ptr, col, val, tile_row, ntiles, skew_a, hints, x, yin, y, u0, fin, dst);
+    case EPI_DOT1:    return launch_one<EPI_DOT1, ACC>(c, row_ptr, col, val, tile_row, ntiles, skew_a, hints, x, yin, y, u0, fin, dst);
+    case EPI_DOT2_YY: return launch_one<EPI_DOT2_YY, ACC>(c, row_ptr, col, val, tile_row, ntiles, skew_a, hints, x, yin, y, u0, fin, dst);
+    case EPI_RESNORM: return launch_one<EPI_RESNORM, ACC>(c, row_ptr, col, val, tile_row, ntiles, skew_a, hints, x, yin, y, u0, fin, dst);
   }
   return sla_fail(c, SLA_ERR_INVALID, "spmv: unknown epilogue");
 }
@@ -399,7 +430,7 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   if (A->ntiles > SLA_MAX_PARTIALS) return sla_fail(c, SLA_ERR_INVALID, "spmv: matrix has too many tiles");
   if (A->m == 0) return SLA_OK;
   if (A->npanels < 2)
-    return launch_epi<false>(c, epi, A->row_ptr, A->col, A->val, A->tile_row, A->ntiles, x, nullptr, y, u0, fin, dst);
+    return launch_epi<false>(c, epi, A->row_ptr, A->col, A->val, A->tile_row, A->ntiles, A->skew_a, A->hints, x, nullptr, y, u0, fin, dst);
   // column panels in ascending order; the epilogue rides on the last pass
   double* ybuf = y;
   if (epi == EPI_RESNORM) {          // y is not an output of this mode: keep the partial sums in a scratch vector
@@ -413,8 +444,8 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
     const sla_panel& pn = A->panels[p];
     const bool last = p + 1 == A->npanels;
     const int e = last ? epi : EPI_NONE;
-    if (p == 0) SLA_TRY(launch_epi<false>(c, e, pn.row_ptr, pn.col, pn.val, pn.tile_row, pn.ntiles, x, nullptr, ybuf, u0, fin, dst));
-    else        SLA_TRY(launch_epi<true>(c, e, pn.row_ptr, pn.col, pn.val, pn.tile_row, pn.ntiles, x, ybuf, ybuf, u0, fin, dst));
+    if (p == 0) SLA_TRY(launch_epi<false>(c, e, pn.row_ptr, pn.col, pn.val, pn.tile_row, pn.ntiles, pn.skew_a, A->hints, x, nullptr, ybuf, u0, fin, dst));
+    else        SLA_TRY(launch_epi<true>(c, e, pn.row_ptr, pn.col, pn.val, pn.tile_row, pn.ntiles, pn.skew_a, A->hints, x, ybuf, ybuf, u0, fin, dst));
   }
   return SLA_OK;
 }
