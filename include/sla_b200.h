@@ -81,6 +81,16 @@ sla_status sla_csr_from_csr(sla_ctx*, int64_t m, int64_t n, int64_t nnz, const i
 /* synthetic workloads of SURVEY.md §8(d), generated on the device from include/sla_synth.h */
 sla_status sla_csr_generate(sla_ctx*, int kind, int64_t n, int nnz_per_row, uint64_t seed, int64_t band,
                             sla_csr** out);
+/* ---- row-partitioned (multi-GPU) matrices: this rank holds global rows [row_lo, row_hi) with GLOBAL column
+ * indices; vectors hold the matching slice.  sla_csr_col_range reports the columns the block references;
+ * the host plans which contiguous pieces of x travel (sparse_linear_algebra_b200/dist.py) and installs the
+ * plan with sla_csr_set_dist: dir 0 = receive global entries [goff, goff+count) from peer, 1 = send them. */
+sla_status sla_csr_generate_rows(sla_ctx*, int kind, int64_t n, int nnz_per_row, uint64_t seed, int64_t band,
+                                 int64_t row_lo, int64_t row_hi, sla_csr** out);
+sla_status sla_csr_col_range(sla_ctx*, const sla_csr*, int64_t* lo, int64_t* hi);   /* hi < lo: no entries */
+sla_status sla_csr_set_dist(sla_ctx*, sla_csr*, int64_t row0, int nseg, const int* dir, const int* peer,
+                            const int64_t* goff, const int64_t* count);
+sla_status sla_vec_generate_slice(sla_ctx*, int64_t i0, int64_t n, uint64_t seed, sla_vec** out);
 sla_status sla_csr_dims(const sla_csr*, int64_t* m, int64_t* n, int64_t* nnz);
 sla_status sla_csr_to_host(sla_ctx*, const sla_csr*, int32_t* row_ptr, int32_t* col_idx, double* val);
 sla_status sla_csr_transpose(sla_ctx*, const sla_csr*, sla_csr** out);         /* transposeSM  SpMatrix.hs:717-718 (bit-exact) */

@@ -198,8 +198,8 @@ static sla_status check3(sla_ctx* c, const sla_vec* x, const sla_vec* y, const s
 
 extern "C" sla_status sla_spmv(sla_ctx* c, const sla_csr* A, const sla_vec* x, sla_vec* y) {
   if (!c || !A || !x || !y) return SLA_ERR_INVALID;
-  if (A->n != x->n) {   // matVecSD | nc == n ... | otherwise = error   Common.hs:248-250
-    snprintf(c->err, sizeof(c->err), "matVec : mismatched dimensions (%lld,%lld)", (long long)A->n, (long long)x->n);
+  if (csr_xdim(A) != x->n) {   // matVecSD | nc == n ... | otherwise = error   Common.hs:248-250
+    snprintf(c->err, sizeof(c->err), "matVec : mismatched dimensions (%lld,%lld)", (long long)csr_xdim(A), (long long)x->n);
     return SLA_ERR_SIZE_MISMATCH;
   }
   if (A->m != y->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "matVec : output vector has the wrong dimension");
@@ -211,6 +211,7 @@ extern "C" sla_status sla_spmv(sla_ctx* c, const sla_csr* A, const sla_vec* x, s
 
 extern "C" sla_status sla_spmvT(sla_ctx* c, const sla_csr* A, const sla_vec* x, sla_vec* y) {
   if (!c || !A || !x || !y) return SLA_ERR_INVALID;
+  if (A->dist) return sla_fail(c, SLA_ERR_INVALID, "vecMat : the transpose of a row-partitioned matrix is not supported");
   if (A->m != x->n) {   // vecMatSD | n == nr ... | otherwise = error   Common.hs:254-256
     snprintf(c->err, sizeof(c->err), "vecMat : mismatching dimensions (%lld,%lld)", (long long)x->n, (long long)A->m);
     return SLA_ERR_SIZE_MISMATCH;
@@ -303,9 +304,9 @@ static sla_status scratch_vec(sla_ctx* c, sla_vec** slot, int64_t n) {
 // Device staging vectors are cached in the ctx, so a steady-state call does no allocation.
 extern "C" sla_status sla_spmv_host(sla_ctx* c, const sla_csr* A, const double* x_host, double* y_host) {
   if (!c || !A || !x_host || !y_host) return SLA_ERR_INVALID;
-  SLA_TRY(scratch_vec(c, &c->scratch_x, A->n));
+  SLA_TRY(scratch_vec(c, &c->scratch_x, csr_xdim(A)));
   SLA_TRY(scratch_vec(c, &c->scratch_y, A->m));
-  SLA_CUDA(c, cudaMemcpyAsync(c->scratch_x->d, x_host, sizeof(double) * (size_t)A->n, cudaMemcpyHostToDevice, c->stream));
+  SLA_CUDA(c, cudaMemcpyAsync(c->scratch_x->d, x_host, sizeof(double) * (size_t)csr_xdim(A), cudaMemcpyHostToDevice, c->stream));
   SLA_TRY(sla_spmv(c, A, c->scratch_x, c->scratch_y));
   SLA_CUDA(c, cudaMemcpyAsync(y_host, c->scratch_y->d, sizeof(double) * (size_t)A->m, cudaMemcpyDeviceToHost, c->stream));
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -62,8 +62,10 @@ static inline sla_status ew_launch(sla_ctx* c, OP op, int64_t n, Ptrs<OP::NIN> i
   int64_t blocks = ((n >> 1) + EW_THREADS - 1) / EW_THREADS;
   if (blocks < 1) blocks = 1;
   if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;
-  ew_kernel<OP><<<(unsigned)blocks, EW_THREADS, 0, c->stream>>>(op, n, in, out, c->scal, c->partials, c->counter, fin, dst);
+  ew_kernel<OP><<<(unsigned)blocks, EW_THREADS, 0, c->stream>>>(op, n, in, out, c->scal, c->partials, c->counter,
+                                                                OP::NRED > 0 ? fin_for(c, fin) : fin, dst);
   SLA_LAUNCH_CHECK(c);
+  if (OP::NRED > 0) SLA_TRY(sla_dist_finish_reduction(c, OP::NRED, fin, dst));
   return SLA_OK;
 }
 

@@ -16,7 +16,7 @@
 // device scalar slots (doubles living in ctx->scal)
 enum {
   S_RHO = 0, S_D1, S_ALPHA, S_D3, S_D4, S_OMEGA, S_D5, S_BETA, S_RES2, S_TMP0, S_TMP1, S_TMP2, S_NRM,
-  S_RR, S_PP, S_RHO_NEW, S_INVN, S_HCOL = 64 /* .. + SLA_MAX_KRYLOV + 1 : one Hessenberg column */,
+  S_RR, S_PP, S_RHO_NEW, S_INVN, S_RAW = 48 /* .. + 8 : per-rank raw sums awaiting the all-reduce */, S_HCOL = 64 /* .. + SLA_MAX_KRYLOV + 1 : one Hessenberg column */,
   S_HCOL2 = 512 /* .. + SLA_MAX_KRYLOV + 1 : re-orthogonalisation correction (GMRES) */
 };
 
@@ -52,6 +52,15 @@ struct sla_panel {
   int ntiles; int64_t nnz; int skew_a;
 };
 
+// row-partitioned (multi-GPU) matrices: which pieces of x travel before each (#>)   (dist.cu)
+struct sla_xseg { int dir; int peer; int64_t goff; int64_t count; };   // dir 0 = receive, 1 = send
+struct sla_dist_info {
+  int64_t row0;              // global index of the first local row (= first entry of the local x slice)
+  int nseg; sla_xseg* seg;
+  double* xfull;             // n doubles; only the remote entries this rank references are kept current
+  int allgather;             // the plan is a plain all-gather of equal slices
+};
+
 struct sla_csr {
   sla_ctx* ctx;
   int64_t m, n, nnz;
@@ -66,7 +75,11 @@ struct sla_csr {
   int hints;                 // cache-hint bits of the SpMV loads chosen by the plan (spmv.cu)
   int npanels;               // >= 2 when the column-panel copy exists
   sla_panel* panels;         // host array of device pointers
+  sla_dist_info* dist;       // non-null: this is the local row block of a distributed matrix (n = GLOBAL columns)
 };
+
+// dimension a vector must have to be multiplied by A / to receive A's product, on this rank
+static inline int64_t csr_xdim(const sla_csr* A) { return A->dist ? A->m : A->n; }
 
 struct sla_dense {
   sla_ctx* ctx;
@@ -150,7 +163,8 @@ enum {
   FIN_CGS_BETA,        // d = sum0 ; beta = d / rho ; rho = d
   FIN_CGNE_ALPHA,      // rr = sum0, pp = sum1 ; alpha = rr / pp
   FIN_CGNE_BETA,       // rr1 = sum0 ; beta = rr1 / rr ; rr = rr1
-  FIN_NORM_INV         // nrm = sqrt(sum0) ; invn = 1 / nrm
+  FIN_NORM_INV,        // nrm = sqrt(sum0) ; invn = 1 / nrm
+  FIN_DEFER = 0x100    // flag (multi-GPU): only store the raw sums; the host all-reduces, then finalize_kernel runs
 };
 
 __device__ __forceinline__ void finalize_scalars(int fin, int dst, double* scal, const double* sum, int nv) {
@@ -218,7 +232,13 @@ __device__ __forceinline__ void grid_reduce_finish(double (&mine)[NV], double* p
   __syncthreads();
   block_sum<NV>(acc, smem);
   if (threadIdx.x == 0) {
-    finalize_scalars(fin, dst, scal, acc, NV);
+    if (fin & FIN_DEFER) {
+      const int base = (fin & 0xff) == FIN_STORE ? dst : S_RAW;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) scal[base + k] = acc[k];
+    } else {
+      finalize_scalars(fin, dst, scal, acc, NV);
+    }
     *counter = 0u;
   }
 }
@@ -231,6 +251,12 @@ void sla_csr_free_panels(sla_csr* A);
 sla_status sla_csr_alloc(sla_ctx* c, int64_t m, int64_t n, int64_t nnz, sla_csr** out);
 sla_status sla_vec_alloc(sla_ctx* c, int64_t n, sla_vec** out);
 sla_status sla_read_scalars(sla_ctx* c, int first, int count, double* host_out);
+// multi-GPU (dist.cu)
+sla_status sla_dist_finish_reduction(sla_ctx* c, int nv, int fin, int dst);
+sla_status sla_dist_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local);
+sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count);
+void sla_csr_free_dist(sla_csr* A);
+static inline int fin_for(const sla_ctx* c, int fin) { return c->world > 1 ? (fin | FIN_DEFER) : fin; }
 
 // SpMV epilogues
 enum {

@@ -47,6 +47,7 @@ extern "C" void sla_csr_free(sla_csr* A) {
   if (A->ctx) cudaStreamSynchronize(A->ctx->stream);
   if (A->T) sla_csr_free(A->T);
   sla_csr_free_panels(A);
+  sla_csr_free_dist(A);
   cudaFree(A->row_ptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->tile_row);
   delete A;
 }
@@ -164,30 +165,43 @@ __global__ void validate_csr_kernel(const int32_t* __restrict__ row_ptr, const i
 }
 
 // isDiagonalSM: every one of the nrows rows is stored with exactly one entry, on the diagonal
-__global__ void is_diag_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int64_t m, int* __restrict__ notdiag) {
+__global__ void is_diag_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int64_t m, int64_t row0,
+                               int* __restrict__ notdiag) {
   GS_LOOP(r, m) {
     const int s = row_ptr[r], e = row_ptr[r + 1];
-    if (e - s != 1 || col[s] != (int32_t)r) *notdiag = 1;
+    if (e - s != 1 || col[s] != (int32_t)(r + row0)) *notdiag = 1;
   }
 }
 
-__global__ void synth_len_kernel(int kind, int64_t n, int k, int64_t band, int32_t* __restrict__ len) {
-  GS_LOOP(i, n) len[i] = sla_synth_row_len(kind, n, k, band, i);
+// min / max column index stored in the local block (multi-GPU halo planning)
+__global__ void col_range_kernel(const int32_t* __restrict__ col, int64_t nnz, int* __restrict__ lohi) {
+  int mn = 0x7fffffff, mx = -1;
+  GS_LOOP(q, nnz) { const int cidx = col[q]; mn = min(mn, cidx); mx = max(mx, cidx); }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0 && mx >= 0) { atomicMin(&lohi[0], mn); atomicMax(&lohi[1], mx); }
 }
 
-__global__ void synth_fill_kernel(int kind, int64_t n, int k, uint64_t seed, int64_t band,
+// rows [row0, row0 + m) of the n x n synthetic family
+__global__ void synth_len_kernel(int kind, int64_t n, int k, int64_t band, int64_t row0, int64_t m, int32_t* __restrict__ len) {
+  GS_LOOP(i, m) len[i] = sla_synth_row_len(kind, n, k, band, row0 + i);
+}
+
+__global__ void synth_fill_kernel(int kind, int64_t n, int k, uint64_t seed, int64_t band, int64_t row0, int64_t m,
                                   const int32_t* __restrict__ row_ptr, int32_t* __restrict__ col, double* __restrict__ val) {
-  GS_LOOP(i, n) {
+  GS_LOOP(i, m) {
     int64_t cols[SLA_SYNTH_MAX_K];
     double vals[SLA_SYNTH_MAX_K];
-    const int cnt = sla_synth_row(kind, n, k, seed, band, i, cols, vals);
+    const int cnt = sla_synth_row(kind, n, k, seed, band, row0 + i, cols, vals);
     const int s = row_ptr[i];
     for (int q = 0; q < cnt; ++q) { col[s + q] = (int32_t)cols[q]; val[s + q] = vals[q]; }
   }
 }
 
-__global__ void synth_vec_kernel(uint64_t seed, int64_t n, double* __restrict__ x) {
-  GS_LOOP(i, n) x[i] = sla_synth_vec(seed, i);
+__global__ void synth_vec_kernel(uint64_t seed, int64_t i0, int64_t n, double* __restrict__ x) {
+  GS_LOOP(i, n) x[i] = sla_synth_vec(seed, i0 + i);
 }
 
 __global__ void set_last_rowptr_kernel(int32_t* row_ptr, const int32_t* len, int64_t m) {
@@ -332,53 +346,78 @@ extern "C" sla_status sla_csr_transpose(sla_ctx* c, const sla_csr* A, sla_csr** 
 extern "C" sla_status sla_csr_is_diagonal(sla_ctx* c, const sla_csr* A, int* out) {
   if (!c || !A || !out) return SLA_ERR_INVALID;
   if (A->is_diag < 0) {
-    int res = 0;
-    if (A->nnz == A->m) {       // size d == nrows m needs exactly one entry per row
-      DevBuf nd;
-      SLA_CUDA(c, nd.alloc(sizeof(int)));
-      SLA_CUDA(c, cudaMemsetAsync(nd.p, 0, sizeof(int), c->stream));
-      is_diag_kernel<<<gs_blocks(A->m), 256, 0, c->stream>>>(A->row_ptr, A->col, A->m, nd.as<int>());
+    DevBuf nd;
+    SLA_CUDA(c, nd.alloc(sizeof(int)));
+    // size d == nrows m needs exactly one entry per row; every rank of a distributed matrix votes
+    SLA_CUDA(c, cudaMemsetAsync(nd.p, A->nnz == A->m ? 0 : 1, sizeof(int), c->stream));
+    if (A->nnz == A->m && A->m > 0) {
+      is_diag_kernel<<<gs_blocks(A->m), 256, 0, c->stream>>>(A->row_ptr, A->col, A->m, A->dist ? A->dist->row0 : 0, nd.as<int>());
       SLA_LAUNCH_CHECK(c);
-      int h = 0;
-      SLA_CUDA(c, cudaMemcpyAsync(&h, nd.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      SLA_CUDA(c, cudaStreamSynchronize(c->stream));
-      res = h ? 0 : 1;
     }
-    const_cast<sla_csr*>(A)->is_diag = res;
+    if (A->dist) SLA_TRY(sla_dist_allreduce_int(c, nd.as<int>(), 1));
+    int h = 0;
+    SLA_CUDA(c, cudaMemcpyAsync(&h, nd.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+    const_cast<sla_csr*>(A)->is_diag = h ? 0 : 1;
   }
   *out = A->is_diag;
   return SLA_OK;
 }
 
-extern "C" sla_status sla_csr_generate(sla_ctx* c, int kind, int64_t n, int nnz_per_row, uint64_t seed, int64_t band,
-                                       sla_csr** out) {
-  if (!c || !out || n <= 0 || nnz_per_row < 1) return SLA_ERR_INVALID;
+extern "C" sla_status sla_csr_col_range(sla_ctx* c, const sla_csr* A, int64_t* lo, int64_t* hi) {
+  if (!c || !A || !lo || !hi) return SLA_ERR_INVALID;
+  DevBuf b;
+  SLA_CUDA(c, b.alloc(2 * sizeof(int)));
+  const int init[2] = {0x7fffffff, -1};
+  SLA_CUDA(c, cudaMemcpyAsync(b.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  if (A->nnz > 0) {
+    col_range_kernel<<<gs_blocks(A->nnz), 256, 0, c->stream>>>(A->col, A->nnz, b.as<int>());
+    SLA_LAUNCH_CHECK(c);
+  }
+  int h[2];
+  SLA_CUDA(c, cudaMemcpyAsync(h, b.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+  *lo = h[1] < 0 ? 0 : h[0];
+  *hi = h[1] < 0 ? -1 : h[1];      // empty block: hi < lo
+  return SLA_OK;
+}
+
+// rows [row_lo, row_hi) of the n x n synthetic matrix, columns GLOBAL (the local block of a row partition)
+extern "C" sla_status sla_csr_generate_rows(sla_ctx* c, int kind, int64_t n, int nnz_per_row, uint64_t seed, int64_t band,
+                                            int64_t row_lo, int64_t row_hi, sla_csr** out) {
+  if (!c || !out || n <= 0 || nnz_per_row < 1 || row_lo < 0 || row_hi < row_lo || row_hi > n) return SLA_ERR_INVALID;
   if (kind != SLA_GEN_UNIFORM && kind != SLA_GEN_BANDED && kind != SLA_GEN_LAPLACE2D) return sla_fail(c, SLA_ERR_INVALID, "generate: unknown kind");
   if (kind == SLA_GEN_LAPLACE2D && band * band != n) return sla_fail(c, SLA_ERR_INVALID, "generate: laplace2d needs n = band*band");
   if (kind == SLA_GEN_BANDED && band < 1) return sla_fail(c, SLA_ERR_INVALID, "generate: banded needs band >= 1");
   *out = nullptr;
+  const int64_t m = row_hi - row_lo;
+  if ((int64_t)nnz_per_row * m >= (1LL << 31) - 2 * SLA_SPMV_TILE) return sla_fail(c, SLA_ERR_INVALID, "generate: nnz exceeds int32 indexing");
   DevBuf len, rp;
-  SLA_CUDA(c, len.alloc(sizeof(int32_t) * (size_t)n));
-  SLA_CUDA(c, rp.alloc(sizeof(int32_t) * (size_t)(n + 1)));
-  synth_len_kernel<<<gs_blocks(n), 256, 0, c->stream>>>(kind, n, nnz_per_row, band, len.as<int32_t>());
-  SLA_LAUNCH_CHECK(c);
-  size_t tb = 0;
-  SLA_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, len.as<int32_t>(), rp.as<int32_t>(), (int)n, c->stream));
-  DevBuf tmp; SLA_CUDA(c, tmp.alloc(tb));
-  SLA_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, tb, len.as<int32_t>(), rp.as<int32_t>(), (int)n, c->stream));
-  c->launches += 2;
-  set_last_rowptr_kernel<<<1, 32, 0, c->stream>>>(rp.as<int32_t>(), len.as<int32_t>(), n);
-  SLA_LAUNCH_CHECK(c);
+  SLA_CUDA(c, len.alloc(sizeof(int32_t) * (size_t)(m + 1)));
+  SLA_CUDA(c, rp.alloc(sizeof(int32_t) * (size_t)(m + 1)));
   int32_t nnz32 = 0;
-  SLA_CUDA(c, cudaMemcpyAsync(&nnz32, rp.as<int32_t>() + n, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  SLA_CUDA(c, cudaStreamSynchronize(c->stream));
-  // int32 scan overflow guard: recompute the bound in 64 bits
-  if ((int64_t)nnz_per_row * n >= (1LL << 31) - 2 * SLA_SPMV_TILE) return sla_fail(c, SLA_ERR_INVALID, "generate: nnz exceeds int32 indexing");
+  if (m > 0) {
+    synth_len_kernel<<<gs_blocks(m), 256, 0, c->stream>>>(kind, n, nnz_per_row, band, row_lo, m, len.as<int32_t>());
+    SLA_LAUNCH_CHECK(c);
+    size_t tb = 0;
+    SLA_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, len.as<int32_t>(), rp.as<int32_t>(), (int)m, c->stream));
+    DevBuf tmp; SLA_CUDA(c, tmp.alloc(tb));
+    SLA_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, tb, len.as<int32_t>(), rp.as<int32_t>(), (int)m, c->stream));
+    c->launches += 2;
+    set_last_rowptr_kernel<<<1, 32, 0, c->stream>>>(rp.as<int32_t>(), len.as<int32_t>(), m);
+    SLA_LAUNCH_CHECK(c);
+    SLA_CUDA(c, cudaMemcpyAsync(&nnz32, rp.as<int32_t>() + m, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+  } else {
+    SLA_CUDA(c, cudaMemsetAsync(rp.p, 0, sizeof(int32_t), c->stream));
+  }
   sla_csr* A = nullptr;
-  SLA_TRY(sla_csr_alloc(c, n, n, (int64_t)nnz32, &A));
-  SLA_CUDA(c, cudaMemcpyAsync(A->row_ptr, rp.p, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyDeviceToDevice, c->stream));
-  synth_fill_kernel<<<gs_blocks(n), 256, 0, c->stream>>>(kind, n, nnz_per_row, seed, band, A->row_ptr, A->col, A->val);
-  SLA_LAUNCH_CHECK(c);
+  SLA_TRY(sla_csr_alloc(c, m, n, (int64_t)nnz32, &A));
+  SLA_CUDA(c, cudaMemcpyAsync(A->row_ptr, rp.p, sizeof(int32_t) * (size_t)(m + 1), cudaMemcpyDeviceToDevice, c->stream));
+  if (m > 0) {
+    synth_fill_kernel<<<gs_blocks(m), 256, 0, c->stream>>>(kind, n, nnz_per_row, seed, band, row_lo, m, A->row_ptr, A->col, A->val);
+    SLA_LAUNCH_CHECK(c);
+  }
   sla_status s = sla_csr_build_plan(c, A);
   if (s != SLA_OK) { sla_csr_free(A); return s; }
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -386,9 +425,21 @@ extern "C" sla_status sla_csr_generate(sla_ctx* c, int kind, int64_t n, int nnz_
   return SLA_OK;
 }
 
-extern "C" sla_status sla_vec_generate(sla_ctx* c, int64_t n, uint64_t seed, sla_vec** out) {
+extern "C" sla_status sla_csr_generate(sla_ctx* c, int kind, int64_t n, int nnz_per_row, uint64_t seed, int64_t band,
+                                       sla_csr** out) {
+  return sla_csr_generate_rows(c, kind, n, nnz_per_row, seed, band, 0, n, out);
+}
+
+// entries [i0, i0 + n) of the synthetic vector with this seed (i0 = 0 on a single GPU)
+extern "C" sla_status sla_vec_generate_slice(sla_ctx* c, int64_t i0, int64_t n, uint64_t seed, sla_vec** out) {
   SLA_TRY(sla_vec_create(c, n, out));
-  synth_vec_kernel<<<gs_blocks(n), 256, 0, c->stream>>>(seed, n, (*out)->d);
-  SLA_LAUNCH_CHECK(c);
+  if (n > 0) {
+    synth_vec_kernel<<<gs_blocks(n), 256, 0, c->stream>>>(seed, i0, n, (*out)->d);
+    SLA_LAUNCH_CHECK(c);
+  }
   return SLA_OK;
+}
+
+extern "C" sla_status sla_vec_generate(sla_ctx* c, int64_t n, uint64_t seed, sla_vec** out) {
+  return sla_vec_generate_slice(c, 0, n, seed, out);
 }

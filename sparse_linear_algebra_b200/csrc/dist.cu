@@ -1,14 +1,186 @@
-// dist.cu — multi-GPU plumbing (one process per GPU; NCCL over NVLink).  Filled in by the row-partitioned path.
+// dist.cu — multi-GPU plumbing: one process (one sla_ctx) per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// The matrix is row-partitioned: rank p owns a contiguous block of rows (with GLOBAL column indices) and the
+// matching slice of every vector.  Per (#>) the ranks exchange exactly the x entries the plan says they need
+// (a full all-gather when the column support is dense, neighbour halos for banded / stencil matrices);
+// every dot / norm is a local deterministic reduction followed by one small all-reduce, after which a
+// one-thread kernel derives alpha / omega / beta on every rank identically.
 #include "common.cuh"
 
-sla_status sla_dist_attach(sla_ctx* c, const void* nccl_id128) {
-  (void)nccl_id128;
-  return sla_fail(c, SLA_ERR_COMM, "sla_init_dist: multi-GPU support is not built into this library yet");
-}
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is bound at run time (see nccl_bind)
+#include <new>
 
-void sla_dist_detach(sla_ctx* c) { (void)c; }
+// NCCL is bound with dlopen when the first multi-GPU call arrives, not at link time: a process that already
+// holds torch's bundled libnccl.so.2 keeps using that copy (RTLD_NOLOAD), a single-GPU process never loads NCCL,
+// and importing this library can never shadow the NCCL another framework expects.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok;
+};
+static NcclApi g_nccl = {};
+
+static bool nccl_bind() {
+  if (g_nccl.ok) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return false;
+#define BIND(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return false
+  BIND(GetUniqueId, "ncclGetUniqueId"); BIND(CommInitRank, "ncclCommInitRank"); BIND(CommDestroy, "ncclCommDestroy");
+  BIND(AllReduce, "ncclAllReduce"); BIND(AllGather, "ncclAllGather"); BIND(Send, "ncclSend"); BIND(Recv, "ncclRecv");
+  BIND(GroupStart, "ncclGroupStart"); BIND(GroupEnd, "ncclGroupEnd"); BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+  g_nccl.ok = true;
+  return true;
+}
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclAllReduce g_nccl.AllReduce
+#define ncclAllGather g_nccl.AllGather
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclGetErrorString g_nccl.GetErrorString
+
+#define SLA_NCCL(ctx, call)                                                                          \
+  do {                                                                                               \
+    ncclResult_t _r = (call);                                                                        \
+    if (_r != ncclSuccess) {                                                                         \
+      snprintf((ctx)->err, sizeof((ctx)->err), "NCCL error %s at %s:%d (%s)", ncclGetErrorString(_r), \
+               __FILE__, __LINE__, #call);                                                           \
+      return SLA_ERR_COMM;                                                                           \
+    }                                                                                                \
+  } while (0)
 
 extern "C" sla_status sla_nccl_unique_id(void* out128) {
-  (void)out128;
-  return SLA_ERR_COMM;
+  if (!out128) return SLA_ERR_INVALID;
+  if (!nccl_bind()) return SLA_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return SLA_ERR_COMM;
+  memcpy(out128, &id, sizeof(id));
+  return SLA_OK;
+}
+
+sla_status sla_dist_attach(sla_ctx* c, const void* nccl_id128) {
+  if (!nccl_id128) return sla_fail(c, SLA_ERR_INVALID, "sla_init_dist: missing NCCL unique id");
+  if (!nccl_bind()) return sla_fail(c, SLA_ERR_COMM, "sla_init_dist: libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  memcpy(&id, nccl_id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  SLA_CUDA(c, cudaSetDevice(c->device));
+  SLA_NCCL(c, ncclCommInitRank(&comm, c->world, id, c->rank));
+  c->nccl = (void*)comm;
+  return SLA_OK;
+}
+
+void sla_dist_detach(sla_ctx* c) {
+  if (c->nccl) { ncclCommDestroy((ncclComm_t)c->nccl); c->nccl = nullptr; }
+}
+
+// one-thread kernel: the scalar post-processing of a grid reduction, run after the all-reduce
+__global__ void finalize_kernel(int fin, int dst, double* scal, int src, int nv) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double sum[8];
+    for (int k = 0; k < nv && k < 8; ++k) sum[k] = scal[src + k];
+    finalize_scalars(fin, dst, scal, sum, nv);
+  }
+}
+
+// Completes a reduction whose per-rank sums sit in scal[S_RAW .. S_RAW + nv): all-reduce, then finalize.
+sla_status sla_dist_finish_reduction(sla_ctx* c, int nv, int fin, int dst) {
+  if (c->world <= 1) return SLA_OK;
+  ncclComm_t comm = (ncclComm_t)c->nccl;
+  if (fin == FIN_STORE) {
+    // raw sums were written straight to their destination slots
+    SLA_NCCL(c, ncclAllReduce(c->scal + dst, c->scal + dst, (size_t)nv, ncclDouble, ncclSum, comm, c->stream));
+    return SLA_OK;
+  }
+  SLA_NCCL(c, ncclAllReduce(c->scal + S_RAW, c->scal + S_RAW, (size_t)nv, ncclDouble, ncclSum, comm, c->stream));
+  finalize_kernel<<<1, 32, 0, c->stream>>>(fin, dst, c->scal, S_RAW, nv);
+  SLA_LAUNCH_CHECK(c);
+  return SLA_OK;
+}
+
+sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count) {
+  if (c->world <= 1) return SLA_OK;
+  SLA_NCCL(c, ncclAllReduce(d_val, d_val, (size_t)count, ncclInt, ncclSum, (ncclComm_t)c->nccl, c->stream));
+  return SLA_OK;
+}
+
+// ---- x exchange ------------------------------------------------------------------------------------------
+
+void sla_csr_free_dist(sla_csr* A) {
+  if (!A->dist) return;
+  cudaFree(A->dist->xfull);
+  delete[] A->dist->seg;
+  delete A->dist;
+  A->dist = nullptr;
+}
+
+// Declares A a row block of a distributed matrix: local rows are global rows [row0, row0 + m); segments say
+// which contiguous pieces of x travel (dir 0: receive [goff, goff+count) of the global vector from peer;
+// dir 1: send local entries [goff - row0, ...) to peer).  The plan is computed on the host (dist.py).
+extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int nseg, const int* dir, const int* peer,
+                                       const int64_t* goff, const int64_t* count) {
+  if (!c || !A || nseg < 0 || (nseg > 0 && (!dir || !peer || !goff || !count))) return SLA_ERR_INVALID;
+  if (row0 < 0 || row0 + A->m > A->n) return sla_fail(c, SLA_ERR_INVALID, "set_dist: local row block lies outside the global index range");
+  sla_csr_free_dist(A);
+  sla_dist_info* d = new (std::nothrow) sla_dist_info();
+  if (!d) return sla_fail(c, SLA_ERR_ALLOC, "set_dist alloc");
+  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0;
+  d->seg = new sla_xseg[nseg > 0 ? nseg : 1];
+  for (int s = 0; s < nseg; ++s) {
+    if (peer[s] < 0 || peer[s] >= c->world || peer[s] == c->rank || goff[s] < 0 || count[s] < 0 || goff[s] + count[s] > A->n ||
+        (dir[s] == 1 && (goff[s] < row0 || goff[s] + count[s] > row0 + A->m))) {
+      delete[] d->seg; delete d;
+      return sla_fail(c, SLA_ERR_INVALID, "set_dist: bad exchange segment");
+    }
+    d->seg[s].dir = dir[s]; d->seg[s].peer = peer[s]; d->seg[s].goff = goff[s]; d->seg[s].count = count[s];
+  }
+  if (cudaMalloc(&d->xfull, sizeof(double) * (size_t)((A->n + 2) & ~(int64_t)1)) != cudaSuccess) {
+    cudaGetLastError(); delete[] d->seg; delete d;
+    return sla_fail(c, SLA_ERR_ALLOC, "set_dist: cudaMalloc failed for the gathered x buffer");
+  }
+  cudaMemsetAsync(d->xfull, 0, sizeof(double) * (size_t)A->n, c->stream);
+  // uniform partition + every peer sends its whole block to everybody = an all-gather
+  if (c->world > 1 && A->n % c->world == 0 && A->m == A->n / c->world && row0 == (int64_t)c->rank * A->m) {
+    int full = 0;
+    for (int s = 0; s < nseg; ++s)
+      if (d->seg[s].dir == 0 && d->seg[s].count == A->m && d->seg[s].goff == (int64_t)d->seg[s].peer * A->m) ++full;
+    if (full == c->world - 1) d->allgather = 1;
+  }
+  A->dist = d;
+  return SLA_OK;
+}
+
+// brings the remote x entries this rank's rows reference into A->dist->xfull
+sla_status sla_dist_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local) {
+  const sla_dist_info* d = A->dist;
+  if (!d || c->world <= 1) return SLA_OK;
+  ncclComm_t comm = (ncclComm_t)c->nccl;
+  if (d->allgather) {
+    SLA_NCCL(c, ncclAllGather(x_local, d->xfull, (size_t)A->m, ncclDouble, comm, c->stream));
+    return SLA_OK;
+  }
+  SLA_NCCL(c, ncclGroupStart());
+  for (int s = 0; s < d->nseg; ++s) {
+    const sla_xseg& g = d->seg[s];
+    if (g.count == 0) continue;
+    if (g.dir == 0) SLA_NCCL(c, ncclRecv(d->xfull + g.goff, (size_t)g.count, ncclDouble, g.peer, comm, c->stream));
+    else            SLA_NCCL(c, ncclSend(x_local + (g.goff - d->row0), (size_t)g.count, ncclDouble, g.peer, comm, c->stream));
+  }
+  SLA_NCCL(c, ncclGroupEnd());
+  return SLA_OK;
 }

@@ -59,11 +59,11 @@ extern "C" sla_status sla_krylov_get(sla_ctx* c, const sla_krylov* st, int field
 
 static sla_status check_system(sla_ctx* c, const char* who, const sla_csr* A, const sla_vec* b, const sla_vec* x0) {
   if (!c || !A || !b || !x0) return SLA_ERR_INVALID;
-  if (A->n != x0->n) {       // aa #> x0 : matVec dimension check   Common.hs:248-250
+  if (csr_xdim(A) != x0->n) {       // aa #> x0 : matVec dimension check   Common.hs:248-250
     snprintf(c->err, sizeof(c->err), "%s: matVec : mismatched dimensions (%lld,%lld)", who, (long long)A->n, (long long)x0->n);
     return SLA_ERR_SIZE_MISMATCH;
   }
-  if (A->m != b->n || A->m != A->n) {
+  if (A->m != b->n || A->m != csr_xdim(A)) {
     snprintf(c->err, sizeof(c->err), "%s: Matrix-vector dimensions are incompatible: Matrix is (%lld,%lld), whereas vector is %lld",
              who, (long long)A->m, (long long)A->n, (long long)b->n);
     return SLA_ERR_SIZE_MISMATCH;
@@ -117,7 +117,7 @@ extern "C" sla_status sla_bicgstab_init(sla_ctx* c, const sla_csr* A, const sla_
 
 extern "C" sla_status sla_bicgstab_step(sla_ctx* c, const sla_csr* A, const sla_vec* r0hat, sla_krylov* st) {
   if (!c || !A || !r0hat || !st || st->kind != SLA_BICGSTAB_) return SLA_ERR_INVALID;
-  if (A->m != st->n || A->n != st->n || r0hat->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "bicgstabStep: dimensions differ");
+  if (A->m != st->n || csr_xdim(A) != st->n || r0hat->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "bicgstabStep: dimensions differ");
   const int64_t n = st->n;
   double *x = st->x->d, *r = st->r->d, *p = st->p->d, *aap = st->t0->d, *s = st->t1->d, *aas = st->t2->d;
   SLA_TRY(ensure_rho(c, st, r0hat));
@@ -153,7 +153,7 @@ extern "C" sla_status sla_cgs_init(sla_ctx* c, const sla_csr* A, const sla_vec* 
 
 extern "C" sla_status sla_cgs_step(sla_ctx* c, const sla_csr* A, const sla_vec* rhat, sla_krylov* st) {
   if (!c || !A || !rhat || !st || st->kind != SLA_CGS_) return SLA_ERR_INVALID;
-  if (A->m != st->n || A->n != st->n || rhat->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgsStep: dimensions differ");
+  if (A->m != st->n || csr_xdim(A) != st->n || rhat->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgsStep: dimensions differ");
   const int64_t n = st->n;
   double *x = st->x->d, *r = st->r->d, *p = st->p->d, *u = st->u->d, *t0 = st->t0->d, *q = st->t1->d, *upq = st->t2->d;
   SLA_TRY(ensure_rho(c, st, rhat));
@@ -186,6 +186,7 @@ extern "C" sla_status sla_cgne_init(sla_ctx* c, const sla_csr* A, const sla_vec*
   if (!out) return SLA_ERR_INVALID;
   *out = nullptr;
   SLA_TRY(check_system(c, "cgneInit", A, b, x0));
+  if (A->dist) return sla_fail(c, SLA_ERR_INVALID, "cgneInit: the transpose of a row-partitioned matrix is not supported");
   SLA_TRY(ensure_transpose(c, A));
   sla_krylov* st = nullptr;
   SLA_TRY(krylov_alloc(c, SLA_CGNE_, A->m, false, &st));
@@ -199,6 +200,7 @@ extern "C" sla_status sla_cgne_init(sla_ctx* c, const sla_csr* A, const sla_vec*
 
 extern "C" sla_status sla_cgne_step(sla_ctx* c, const sla_csr* A, sla_krylov* st) {
   if (!c || !A || !st || st->kind != SLA_CGNE_) return SLA_ERR_INVALID;
+  if (A->dist) return sla_fail(c, SLA_ERR_INVALID, "cgneStep: the transpose of a row-partitioned matrix is not supported");
   if (A->m != st->n || A->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgneStep: dimensions differ");
   SLA_TRY(ensure_transpose(c, A));
   const int64_t n = st->n;
@@ -247,7 +249,7 @@ extern "C" sla_status sla_linsolve0(sla_ctx* c, int method, const sla_csr* A, co
              (long long)A->m, (long long)A->n, (long long)b->n);
     return SLA_ERR_SIZE_MISMATCH;
   }
-  if (x->n != A->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "linSolve0 : output vector has the wrong dimension");
+  if (x->n != csr_xdim(A)) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "linSolve0 : output vector has the wrong dimension");
   int diag = 0;
   SLA_TRY(sla_csr_is_diagonal(c, A, &diag));
   if (diag) {                                 // isDiagonalSM aa' = return $ reciprocal aa' #> b'   :1024-1025
@@ -421,9 +423,11 @@ static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j
       const int nc = nq - k0 < TS_CH ? nq - k0 : TS_CH;
       tsmv_t_kernel<<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, slot0);
       SLA_LAUNCH_CHECK(c);
+      SLA_TRY(sla_dist_finish_reduction(c, nc, FIN_STORE, slot0 + k0));
     }
-    lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, FIN_NORM_INV, slot0);
+    lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, fin_for(c, FIN_NORM_INV), slot0);
     SLA_LAUNCH_CHECK(c);
+    SLA_TRY(sla_dist_finish_reduction(c, 1, FIN_NORM_INV, 0));
   }
   // q_{j+1} = (recip h_{j+1,j}) .* w
   { Ptrs<1> in{{w}}; Ptrs<1> o{{Q->d + (int64_t)(j + 1) * ld}}; OpScaleDev op; op.slot = S_INVN; op.a = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
@@ -440,12 +444,12 @@ static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j
 extern "C" sla_status sla_arnoldi(sla_ctx* c, const sla_csr* A, const sla_vec* b, int kn, sla_dense** Qout, double* h_host, int* nmax_out) {
   if (!c || !A || !b || !Qout || !h_host || !nmax_out) return SLA_ERR_INVALID;
   *Qout = nullptr; *nmax_out = 0;
-  if (A->n != b->n) {                      // | n == nb ... | otherwise = throwM (MatVecSizeMismatchException "arnoldi" (m,n) nb)   :636-637
+  if (csr_xdim(A) != b->n) {               // | n == nb ... | otherwise = throwM (MatVecSizeMismatchException "arnoldi" (m,n) nb)   :636-637
     snprintf(c->err, sizeof(c->err), "arnoldi : Matrix-vector dimensions are incompatible: Matrix is (%lld,%lld) , whereas vector is %lld",
              (long long)A->m, (long long)A->n, (long long)b->n);
     return SLA_ERR_SIZE_MISMATCH;
   }
-  if (A->m != A->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "arnoldi : matrix must be square");
+  if (A->m != csr_xdim(A)) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "arnoldi : matrix must be square");
   if (kn < 2 || kn > SLA_MAX_KRYLOV)       // kn <= 1 never meets `i == kn` and runs to breakdown in the reference; not supported here
     return sla_fail(c, SLA_ERR_INVALID, "arnoldi : kn must be in [2, 384]");
   const int64_t n = A->m;

@@ -92,12 +92,14 @@ __device__ __forceinline__ void row_epilogue(int r, double acc, double* y, const
 }
 
 // ACC = false: row sums start from 0.0.  ACC = true: they continue from yin[r] (a later column panel).
-template <int TILE, int EPI, bool ACC>
+// DIST = true (row block of a multi-GPU matrix, GLOBAL column indices): columns inside [col0, col0 + ncl) are
+// read from the local slice x, every other column from the exchanged buffer xr.
+template <int TILE, int EPI, bool ACC, bool DIST>
 __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val,
                  const double* __restrict__ x, const double* yin, double* y, const int* __restrict__ tile_row,
                  const double* __restrict__ u0, double* partials, unsigned int* counter, double* scal,
-                 int fin, int dst, int hints) {
+                 int fin, int dst, int hints, const double* __restrict__ xr, int col0, int ncl) {
   constexpr int PER = TILE / SPMV_THREADS;                // entries per thread, lane-contiguous
   __shared__ double prod[TILE + TILE / 8];              // keep CTA smem small: the L1 left over holds the in-flight gathers
   __shared__ double red[2 * 32];
@@ -126,8 +128,11 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
     }
     double xv[PER];
 #pragma unroll
-    for (int it = 0; it < PER; ++it)
-      xv[it] = (hints & 4) ? ld_keep_double_na(x + c[it], pol_keep) : ld_keep_double(x + c[it], pol_keep);
+    for (int it = 0; it < PER; ++it) {
+      const double* src = x + c[it];
+      if (DIST) src = (unsigned)(c[it] - col0) < (unsigned)ncl ? x + (c[it] - col0) : xr + c[it];
+      xv[it] = (hints & 4) ? ld_keep_double_na(src, pol_keep) : ld_keep_double(src, pol_keep);
+    }
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
       const int k = it * SPMV_THREADS + tid;
@@ -152,7 +157,9 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
     for (int k = ks; k < kin; ++k) acc = __dadd_rn(acc, prod[skew(k, sk)]);
     for (int k = (ks > TILE ? ks : TILE); k < ke; ++k) {     // tail beyond the tile (last owned row only)
       const int g = base + k;
-      acc = __dadd_rn(acc, __dmul_rn(val[g], x[col[g]]));
+      const int cg = col[g];
+      const double xg = DIST ? ((unsigned)(cg - col0) < (unsigned)ncl ? x[cg - col0] : xr[cg]) : x[cg];
+      acc = __dadd_rn(acc, __dmul_rn(val[g], xg));
     }
     row_epilogue<EPI>(r, acc, y, u0, e0, e1);
   }
@@ -169,7 +176,12 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
       for (int k = ks + lane; k < ke; k += 32) {
         double t;
         if (k < TILE) t = prod[skew(k, sk)];
-        else { const int g = base + k; t = __dmul_rn(val[g], x[col[g]]); }
+        else {
+          const int g = base + k;
+          const int cg = col[g];
+          const double xg = DIST ? ((unsigned)(cg - col0) < (unsigned)ncl ? x[cg - col0] : xr[cg]) : x[cg];
+          t = __dmul_rn(val[g], xg);
+        }
         acc += t;
       }
       acc = warp_sum(acc);
@@ -395,42 +407,61 @@ sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
   return build_panels(c, A, want);
 }
 
-template <int EPI, bool ACC>
-static sla_status launch_one(sla_ctx* c, const int32_t* row_ptr, const int32_t* col, const double* val, const int32_t* tile_row,
-                             int ntiles, int skew_a, int hints, const double* x, const double* yin, double* y, const double* u0, int fin, int dst) {
+// everything one launch needs besides the epilogue selection
+struct SpmvArgs {
+  const int32_t *row_ptr, *col, *tile_row; const double* val;
+  int ntiles, skew_a, hints;
+  const double *x, *yin; double* y; const double* u0;
+  int fin, dst;
+  const double* xr; int col0, ncl;     // DIST only
+};
+
+template <int EPI, bool ACC, bool DIST>
+static sla_status launch_one(sla_ctx* c, const SpmvArgs& a) {
   static int carve_set = 0;
   if (!carve_set) {
     carve_set = 1;
     if (const char* e = getenv("SLA_SPMV_CARVEOUT"))
-      cudaFuncSetAttribute(spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+      cudaFuncSetAttribute(spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
   }
-  spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC><<<ntiles, SPMV_THREADS, 0, c->stream>>>(
-      row_ptr, col, val, x, yin, y, tile_row, u0, c->partials, c->counter, c->scal, fin, dst, (hints & 0xff) | (skew_a << 8));
+  spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST><<<a.ntiles, SPMV_THREADS, 0, c->stream>>>(
+      a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, c->counter, c->scal,
+      EPI != EPI_NONE ? fin_for(c, a.fin) : a.fin, a.dst, (a.hints & 0xff) | (a.skew_a << 8), a.xr, a.col0, a.ncl);
   SLA_LAUNCH_CHECK(c);
+  if (EPI != EPI_NONE) SLA_TRY(sla_dist_finish_reduction(c, 2, a.fin, a.dst));
   return SLA_OK;
 }
 
-template <bool ACC>
-static sla_status launch_epi(sla_ctx* c, int epi, const int32_t* row_ptr, const int32_t* col, const double* val,
-                             const int32_t* tile_row, int ntiles, int skew_a, int hints, const double* x, const double* yin, double* y,
-                             const double* u0, int fin, int dst) {
+template <bool ACC, bool DIST>
+static sla_status launch_epi(sla_ctx* c, int epi, const SpmvArgs& a) {
   switch (epi) {
-    case EPI_NONE:    return launch_one<EPI_NONE, ACC>(c, row_ptr, col, val, tile_row, ntiles, skew_a, hints, x, yin, y, u0, fin, dst);
-    case EPI_DOT1:    return launch_one<EPI_DOT1, ACC>(c, row_ptr, col, val, tile_row, ntiles, skew_a, hints, x, yin, y, u0, fin, dst);
-    case EPI_DOT2_YY: return launch_one<EPI_DOT2_YY, ACC>(c, row_ptr, col, val, tile_row, ntiles, skew_a, hints, x, yin, y, u0, fin, dst);
-    case EPI_RESNORM: return launch_one<EPI_RESNORM, ACC>(c, row_ptr, col, val, tile_row, ntiles, skew_a, hints, x, yin, y, u0, fin, dst);
+    case EPI_NONE:    return launch_one<EPI_NONE, ACC, DIST>(c, a);
+    case EPI_DOT1:    return launch_one<EPI_DOT1, ACC, DIST>(c, a);
+    case EPI_DOT2_YY: return launch_one<EPI_DOT2_YY, ACC, DIST>(c, a);
+    case EPI_RESNORM: return launch_one<EPI_RESNORM, ACC, DIST>(c, a);
   }
   return sla_fail(c, SLA_ERR_INVALID, "spmv: unknown epilogue");
 }
 
+static sla_status launch_any(sla_ctx* c, int epi, bool acc, bool dist, const SpmvArgs& a) {
+  if (dist) return acc ? launch_epi<true, true>(c, epi, a) : launch_epi<false, true>(c, epi, a);
+  return acc ? launch_epi<true, false>(c, epi, a) : launch_epi<false, false>(c, epi, a);
+}
+
 // y = A x with an optional fused epilogue.  u1 is reserved (EPI_DOT2_YY uses y itself).
+// For a row block of a distributed matrix, x is the LOCAL slice; the remote entries are exchanged first.
 sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi,
                            const double* u0, const double* u1, int fin, int dst) {
   (void)u1;
   if (A->ntiles > SLA_MAX_PARTIALS) return sla_fail(c, SLA_ERR_INVALID, "spmv: matrix has too many tiles");
-  if (A->m == 0) return SLA_OK;
-  if (A->npanels < 2)
-    return launch_epi<false>(c, epi, A->row_ptr, A->col, A->val, A->tile_row, A->ntiles, A->skew_a, A->hints, x, nullptr, y, u0, fin, dst);
+  const bool dist = A->dist != nullptr;
+  if (dist) SLA_TRY(sla_dist_exchange_x(c, A, x));          // every rank takes part, even with no local rows
+  SpmvArgs a;
+  a.row_ptr = A->row_ptr; a.col = A->col; a.val = A->val; a.tile_row = A->tile_row;
+  a.ntiles = A->ntiles; a.skew_a = A->skew_a; a.hints = A->hints;
+  a.x = x; a.yin = nullptr; a.y = y; a.u0 = u0; a.fin = fin; a.dst = dst;
+  a.xr = dist ? A->dist->xfull : nullptr; a.col0 = dist ? (int)A->dist->row0 : 0; a.ncl = dist ? (int)A->m : 0;
+  if (A->npanels < 2) return launch_any(c, epi, false, dist, a);
   // column panels in ascending order; the epilogue rides on the last pass
   double* ybuf = y;
   if (epi == EPI_RESNORM) {          // y is not an output of this mode: keep the partial sums in a scratch vector
@@ -443,9 +474,10 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   for (int p = 0; p < A->npanels; ++p) {
     const sla_panel& pn = A->panels[p];
     const bool last = p + 1 == A->npanels;
-    const int e = last ? epi : EPI_NONE;
-    if (p == 0) SLA_TRY(launch_epi<false>(c, e, pn.row_ptr, pn.col, pn.val, pn.tile_row, pn.ntiles, pn.skew_a, A->hints, x, nullptr, ybuf, u0, fin, dst));
-    else        SLA_TRY(launch_epi<true>(c, e, pn.row_ptr, pn.col, pn.val, pn.tile_row, pn.ntiles, pn.skew_a, A->hints, x, ybuf, ybuf, u0, fin, dst));
+    a.row_ptr = pn.row_ptr; a.col = pn.col; a.val = pn.val; a.tile_row = pn.tile_row;
+    a.ntiles = pn.ntiles; a.skew_a = pn.skew_a;
+    a.yin = p == 0 ? nullptr : ybuf; a.y = ybuf;
+    SLA_TRY(launch_any(c, last ? epi : EPI_NONE, p > 0, dist, a));
   }
   return SLA_OK;
 }

@@ -1,0 +1,133 @@
+"""Multi-GPU host logic: one process per GPU (torchrun), row-partitioned matrices, NCCL over NVLink.
+
+torch.distributed is the plumbing (rendezvous, broadcasting the NCCL id, gathering the per-rank column
+ranges); the data path — the x exchange before each (#>) and the all-reduce behind every dot — runs inside
+libsla_b200.so on the library's own communicator and stream.
+
+The planning functions (`row_partition`, `plan_exchange`) are pure Python and are exercised on CPU with the
+gloo backend (tests/test_dist_cpu.py).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .sparse import Context, SpMatrix, SpVector, set_default_context
+
+
+def row_partition(n, world):
+    """Contiguous row blocks, balanced by rows: rank p owns [starts[p], starts[p+1])."""
+    return [(n * p) // world for p in range(world + 1)]
+
+
+def _overlap(lo, hi, a, b):
+    """Intersection of the inclusive range [lo, hi] with the half-open block [a, b) as (offset, count)."""
+    s, e = max(lo, a), min(hi + 1, b)
+    return (s, e - s) if e > s else None
+
+
+def plan_exchange(rank, starts, needs):
+    """Which contiguous pieces of x travel before a (#>).
+
+    starts : the row partition (world + 1 entries), identical on every rank.
+    needs  : per rank, the inclusive range (lo, hi) of GLOBAL columns its row block references
+             (hi < lo when the block is empty).
+    Returns [(dir, peer, goff, count)]: dir 0 = this rank receives global entries [goff, goff+count) from
+    peer, dir 1 = this rank sends them.  A rank never exchanges with itself; its own slice is read in place.
+    Every send on rank a to rank b has the matching receive on rank b from a, because both are derived from
+    the same `needs` table.
+    """
+    world = len(starts) - 1
+    segs = []
+    for q in range(world):
+        if q == rank:
+            continue
+        lo, hi = needs[rank]
+        if hi >= lo:
+            ov = _overlap(lo, hi, starts[q], starts[q + 1])
+            if ov:
+                segs.append((0, q, ov[0], ov[1]))
+        lo, hi = needs[q]
+        if hi >= lo:
+            ov = _overlap(lo, hi, starts[rank], starts[rank + 1])
+            if ov:
+                segs.append((1, q, ov[0], ov[1]))
+    return segs
+
+
+def exchange_bytes(segs):
+    """(bytes received, bytes sent) per (#>) under this plan."""
+    return (8 * sum(c for d, _, _, c in segs if d == 0), 8 * sum(c for d, _, _, c in segs if d == 1))
+
+
+def init_context(device=None):
+    """Create this rank's Context inside an initialised torch.distributed job (any backend).
+
+    Rank 0 draws the NCCL unique id from the library, torch.distributed broadcasts it, every rank joins."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        ctx = Context(device)
+        set_default_context(ctx)
+        return ctx
+    lib = L.load()
+    box = [None]
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        st = lib.sla_nccl_unique_id(buf)
+        if st != L.SLA_OK:
+            raise RuntimeError("sla_nccl_unique_id failed: libnccl.so.2 not loadable")
+        box[0] = bytes(buf.raw)
+    dist.broadcast_object_list(box, src=0)
+    ctx = Context(device, rank=rank, world=world, nccl_id=box[0])
+    set_default_context(ctx)
+    return ctx
+
+
+def _install_plan(ctx, A, row0, segs):
+    n = len(segs)
+    dirs = (C.c_int * max(n, 1))(*[s[0] for s in segs])
+    peers = (C.c_int * max(n, 1))(*[s[1] for s in segs])
+    goff = (C.c_int64 * max(n, 1))(*[s[2] for s in segs])
+    cnt = (C.c_int64 * max(n, 1))(*[s[3] for s in segs])
+    ctx.check(ctx.lib.sla_csr_set_dist(ctx.h, A.h, row0, n, dirs, peers, goff, cnt))
+
+
+def distribute(ctx, A, starts):
+    """Turn the local row block A (global column indices) into a distributed matrix: gather every rank's
+    column range, plan the exchange, install it.  Collective over torch.distributed."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = C.c_int64(0), C.c_int64(-1)
+    ctx.check(ctx.lib.sla_csr_col_range(ctx.h, A.h, C.byref(lo), C.byref(hi)))
+    needs = [None] * world
+    dist.all_gather_object(needs, (lo.value, hi.value))
+    segs = plan_exchange(rank, starts, needs)
+    _install_plan(ctx, A, starts[rank], segs)
+    A.dist_plan = segs
+    A.row_starts = starts
+    return A
+
+
+def generate_distributed(ctx, kind, n, nnz_per_row, seed, band=0):
+    """Rank-local block of the n x n synthetic family (include/sla_synth.h), row-partitioned over the job."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    starts = row_partition(n, world)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.sla_csr_generate_rows(ctx.h, kind, n, nnz_per_row, seed, band, starts[rank], starts[rank + 1], C.byref(h)))
+    A = SpMatrix(ctx, h)
+    if world > 1:
+        distribute(ctx, A, starts)
+    else:
+        A.row_starts = starts
+    return A
+
+
+def generate_vector_slice(ctx, n, seed, starts, rank):
+    h = C.c_void_p()
+    ctx.check(ctx.lib.sla_vec_generate_slice(ctx.h, starts[rank], starts[rank + 1] - starts[rank], seed, C.byref(h)))
+    return SpVector(ctx, h)

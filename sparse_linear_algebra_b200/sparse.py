@@ -496,7 +496,7 @@ def _opts(nits, tol_abs, tol_rel, true_residual, check_every):
 def linSolve0(method, aa, b, x0, nits=0, tol_abs=0.0, tol_rel=0.0, true_residual=True, check_every=1, info=False):
     """linSolve0 method aa b x0 (Sparse.hs:1016-1072): nits = 200, tol = max 1e-6 (1e-4 * ||r0||), true residual."""
     ctx = aa.ctx
-    x = SpVector.zeroSV(aa.ncols, ctx)
+    x = SpVector.zeroSV(x0.dim, ctx)
     o = _opts(nits, tol_abs, tol_rel, true_residual, check_every)
     iters, res = C.c_int(0), C.c_double(0)
     ctx.check(ctx.lib.sla_linsolve0(ctx.h, method, aa.h, b.h, x0.h, C.byref(o), x.h, C.byref(iters), C.byref(res)))
@@ -530,7 +530,7 @@ def arnoldi(aa, b, kn):
 
 def gmres(aa, b, x0, restart=30, nits=0, tol_abs=0.0, tol_rel=0.0, info=False):
     ctx = aa.ctx
-    x = SpVector.zeroSV(aa.ncols, ctx)
+    x = SpVector.zeroSV(x0.dim, ctx)
     o = _opts(nits, tol_abs, tol_rel, True, 1)
     iters, res = C.c_int(0), C.c_double(0)
     ctx.check(ctx.lib.sla_gmres(ctx.h, aa.h, b.h, x0.h, restart, C.byref(o), x.h, C.byref(iters), C.byref(res)))
@@ -539,4 +539,4 @@ def gmres(aa, b, x0, restart=30, nits=0, tol_abs=0.0, tol_rel=0.0, info=False):
 
 def backslash(aa, b):
     """aa <\\> b: the commented-out LinearSystem instance uses GMRES with x0 = 0.1 (Sparse.hs:1082-1088)."""
-    return gmres(aa, b, SpVector.constv(aa.ncols, 0.1, aa.ctx), restart=30)
+    return gmres(aa, b, SpVector.constv(b.dim, 0.1, aa.ctx), restart=30)

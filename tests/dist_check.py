@@ -1,0 +1,93 @@
+"""Multi-rank parity check, launched by tests/test_gpu_dist.py (or by hand):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_check.py
+Every rank holds a row block; results are compared with the single-process CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import sparse_linear_algebra_b200 as sla
+    from sparse_linear_algebra_b200 import dist as sd
+    from oracle import oracle as ora
+
+    ctx = sd.init_context(local)
+    seed = 0x5EED0006
+    fails = []
+
+    def check(name, cond):
+        if not cond:
+            fails.append(f"rank {rank}: {name}")
+
+    cases = [("uniform", sla.GEN_UNIFORM, ora.GEN_UNIFORM, 20000, 16, 0),
+             ("banded", sla.GEN_BANDED, ora.GEN_BANDED, 30000, 16, 300),
+             ("laplace", sla.GEN_LAPLACE2D, ora.GEN_LAPLACE2D, 96 * 96, 5, 96),
+             ("ragged", sla.GEN_UNIFORM, ora.GEN_UNIFORM, 1001, 8, 0)]
+    for name, gk, ok_, n, k, band in cases:
+        A = sd.generate_distributed(ctx, gk, n, k, seed, band)
+        starts = A.row_starts
+        r0, r1 = starts[rank], starts[rank + 1]
+        x = sd.generate_vector_slice(ctx, n, seed + 1, starts, rank)
+        Ao = ora.SpMatrix.synth(ok_, n, k, seed, band)
+        xo = ora.SpVector.synth(seed + 1, n)
+        y = (A @ x).toDenseListSV()
+        yo = Ao.matVec(xo).toDenseListSV()
+        check(f"{name}: row-partitioned (#>) bit-exact", y.tobytes() == yo[r0:r1].tobytes())
+        # <.> and norm2 across ranks
+        d, do = x.dot(A @ x), xo.dot(Ao.matVec(xo))
+        check(f"{name}: distributed <.>", abs(d - do) <= 1e-12 * abs(do) + 1e-300)
+        check(f"{name}: distributed norm2", abs(x.norm2() - xo.norm2()) <= 1e-13 * xo.norm2())
+        # BiCGSTAB / CGS trajectories, 4 steps
+        b, bo = A @ x, Ao.matVec(xo)
+        for init, step, oinit, ostep in ((sla.bicgsInit, sla.bicgstabStep, ora.bicgsInit, ora.bicgstabStep),
+                                         (sla.cgsInit, sla.cgsStep, ora.cgsInit, ora.cgsStep)):
+            st = init(A, b, sla.SpVector.zeroSV(r1 - r0))
+            x0o = ora.SpVector.mkSpVR(n, np.zeros(n))
+            sto = oinit(Ao, bo, x0o)
+            rhat, rhato = st.r.copy(), bo - Ao.matVec(x0o)
+            for it in range(4):
+                step(A, rhat, st)
+                sto = ostep(Ao, rhato, sto)
+                xg, xr = st.x.toDenseListSV(), sto.x.toDenseListSV()
+                check(f"{name}: {step.__name__} iterate {it}", np.abs(xg - xr[r0:r1]).max() <= 1e-10 * np.abs(xr).max())
+        # linSolve0: same iteration count on every rank and as the oracle
+        if name in ("uniform", "ragged"):
+            xs, it, res = sla.linSolve0(sla.BICGSTAB_, A, b, sla.SpVector.constv(r1 - r0, 0.1), info=True)
+            xso, ito, _ = ora.linSolve0(ora.BICGSTAB_, Ao, bo, ora.SpVector.mkSpVR(n, [0.1] * n), info=True)
+            check(f"{name}: linSolve0 iteration count {it} vs {ito}", it == ito)
+            check(f"{name}: linSolve0 solution", np.abs(xs.toDenseListSV() - xso.toDenseListSV()[r0:r1]).max() <= 1e-10)
+            xg_, itg, resg = sla.gmres(A, b, sla.SpVector.zeroSV(r1 - r0), restart=20, tol_abs=1e-10, tol_rel=1e-12, info=True)
+            check(f"{name}: gmres residual {resg}", resg <= 1e-8)
+        # arnoldi: H equals the oracle's while the basis is well conditioned
+        Qd, H, brk = sla.arnoldi(A, x, 6)
+        Qo, Ho = ora.arnoldi(Ao, xo, 6)
+        check(f"{name}: arnoldi H", H.shape == Ho.shape and np.abs(H - Ho).max() <= 1e-9 * np.abs(Ho).max())
+        check(f"{name}: arnoldi Q slice", np.abs(Qd.toHost() - Qo[r0:r1, :]).max() <= 1e-9)
+    # the diagonal shortcut of linSolve0 needs every rank's vote
+    n = 1000
+    starts = sd.row_partition(n, world)
+    all_fails = [None] * world
+    dist.all_gather_object(all_fails, fails)
+    flat = [f for fl in all_fails for f in fl]
+    if rank == 0:
+        print("DIST_CHECK", "OK" if not flat else "FAIL", f"world={world}", flush=True)
+        for f in flat:
+            print("  ", f, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if flat else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+"""CPU tests of the multi-GPU host logic (world_size 2, gloo): the row partition and the x-exchange plan that
+libsla_b200.so executes with NCCL on the device are computed by sparse_linear_algebra_b200.dist; here the same
+plan is executed with gloo send/recv on numpy slices and the row-partitioned product, computed per rank by the
+oracle, must equal the single-process oracle product bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_row_partition_and_plan_unit():
+    from sparse_linear_algebra_b200.dist import exchange_bytes, plan_exchange, row_partition
+
+    assert row_partition(10, 3) == [0, 3, 6, 10]
+    assert row_partition(7, 1) == [0, 7]
+    starts = row_partition(100, 4)                       # [0, 25, 50, 75, 100]
+    # banded: every rank needs its own block +- 5 columns
+    needs = [(max(0, starts[p] - 5), min(99, starts[p + 1] - 1 + 5)) for p in range(4)]
+    plans = [plan_exchange(p, starts, needs) for p in range(4)]
+    assert sorted(plans[0]) == [(0, 1, 25, 5), (1, 1, 20, 5)]
+    assert sorted(plans[1]) == [(0, 0, 20, 5), (0, 2, 50, 5), (1, 0, 25, 5), (1, 2, 45, 5)]
+    # every send has its matching receive
+    for p in range(4):
+        for d, q, off, cnt in plans[p]:
+            assert (1 - d, p, off, cnt) in plans[q]
+    assert exchange_bytes(plans[1]) == (80, 80)
+    # dense support: all-gather shape
+    needs = [(0, 99)] * 4
+    pl = plan_exchange(2, starts, needs)
+    assert sorted(s for s in pl if s[0] == 0) == [(0, 0, 0, 25), (0, 1, 25, 25), (0, 3, 75, 25)]
+    assert sorted(s for s in pl if s[0] == 1) == [(1, 0, 50, 25), (1, 1, 50, 25), (1, 3, 50, 25)]
+    # an empty block neither receives nor is sent anything on its behalf
+    needs = [(0, 99), (0, -1), (0, 99), (0, 99)]
+    assert all(s[0] == 1 for s in plan_exchange(1, starts, needs))
+    assert not [s for s in plan_exchange(0, starts, needs) if s[0] == 1 and s[1] == 1]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, kind_name, n, k, band, ret):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as ora
+        from sparse_linear_algebra_b200.dist import plan_exchange, row_partition
+
+        kind = getattr(ora, kind_name)
+        seed = 0x5EED0005
+        starts = row_partition(n, world)
+        r0, r1 = starts[rank], starts[rank + 1]
+        # local row block with GLOBAL column indices
+        rows = [ora.synth_row(kind, n, k, seed, band, i) for i in range(r0, r1)]
+        row_ptr = np.concatenate([[0], np.cumsum([len(c) for c, _ in rows])]).astype(np.int64)
+        col = np.concatenate([c for c, _ in rows]) if rows else np.zeros(0, np.int64)
+        val = np.concatenate([v for _, v in rows]) if rows else np.zeros(0)
+        need = (int(col.min()), int(col.max())) if col.size else (0, -1)
+        needs = [None] * world
+        dist.all_gather_object(needs, need)
+        segs = plan_exchange(rank, starts, needs)
+        # execute the plan with gloo point-to-point copies
+        x_local = ora.SpVector.synth(seed + 1, n).toDenseListSV()[r0:r1].copy()
+        x_full = np.full(n, np.nan)                       # NaN everywhere: touching an un-exchanged entry poisons y
+        x_full[r0:r1] = x_local
+        reqs, bufs = [], []
+        for d, q, off, cnt in segs:
+            if d == 1:
+                reqs.append(dist.isend(torch.from_numpy(x_local[off - r0: off - r0 + cnt].copy()), q))
+        for d, q, off, cnt in segs:
+            if d == 0:
+                t = torch.empty(cnt, dtype=torch.float64)
+                bufs.append((off, cnt, t))
+                reqs.append(dist.irecv(t, q))
+        for r in reqs:
+            r.wait()
+        for off, cnt, t in bufs:
+            x_full[off: off + cnt] = t.numpy()
+        # local product by the oracle on the exchanged vector (absent = never referenced)
+        Aloc = ora.SpMatrix.fromCSR(r1 - r0, n, row_ptr, col, val)
+        xs = ora.SpVector.mkSpVR(n, np.where(np.isnan(x_full), 0.0, x_full))
+        touched = np.zeros(n, bool); touched[col] = True
+        assert not np.isnan(x_full[touched]).any(), "the plan left a referenced x entry un-exchanged"
+        y_local = Aloc.matVec(xs).toDenseListSV()
+        ys = [None] * world
+        dist.all_gather_object(ys, y_local)
+        plans = [None] * world
+        dist.all_gather_object(plans, segs)
+        if rank == 0:
+            Afull = ora.SpMatrix.synth(kind, n, k, seed, band)
+            yref = Afull.matVec(ora.SpVector.synth(seed + 1, n)).toDenseListSV()
+            ok = np.concatenate(ys).tobytes() == yref.tobytes()
+            for p in range(world):
+                for d, q, off, cnt in plans[p]:
+                    ok = ok and (1 - d, p, off, cnt) in plans[q]
+            recv_bytes = [8 * sum(c for d, _, _, c in pl if d == 0) for pl in plans]
+            ret.put((ok, recv_bytes))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,n,k,band", [("GEN_UNIFORM", 600, 8, 0), ("GEN_BANDED", 1000, 8, 12), ("GEN_LAPLACE2D", 24 * 24, 5, 24)])
+def test_row_partitioned_spmv_gloo(ora, kind, n, k, band):
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, k, band, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, recv_bytes = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
+    if kind == "GEN_UNIFORM":
+        assert recv_bytes == [8 * (n // 2)] * 2          # dense support: the whole remote block
+    if kind == "GEN_BANDED":
+        assert max(recv_bytes) <= 8 * band               # halo only
+    if kind == "GEN_LAPLACE2D":
+        assert recv_bytes == [8 * band] * 2              # one grid line from the neighbour
