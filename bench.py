@@ -152,9 +152,13 @@ def run_gpu(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import sparse_linear_algebra_b200 as sla
+    from sparse_linear_algebra_b200 import dist as sd
 
-    ctx = sla.Context(local)
-    sla.set_default_context(ctx)
+    if world > 1:
+        ctx = sd.init_context(local)
+    else:
+        ctx = sla.Context(local)
+        sla.set_default_context(ctx)
 
     def barrier():
         if dist is not None:
@@ -173,88 +177,98 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- config 2: SpMV.  Weak scaling: every rank owns a 10M-row block (replicated family, own seed).
+    def gen(kind, n, k, seed, band=0):
+        if world == 1:
+            A = sla.SpMatrix.generate(kind, n, k, seed, band)
+            A.row_starts = [0, n]
+            return A
+        return sd.generate_distributed(ctx, kind, n, k, seed, band)
+
+    def vec(n, seed, starts):
+        return sd.generate_vector_slice(ctx, n, seed, starts, rank)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = ctx.launches
+        ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_stop()
+        barrier()
+        return max_over_ranks(ms) / steps, ctx.launches - l0
+
+    # ---- config 2: the SAME 10M x 10M matrix at every N (strong scaling), row-partitioned over the ranks;
+    # each (#>) includes the exchange of the x entries the local rows reference.
     n, k = N_CFG2, K_CFG2
-    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, SEED_CFG2 + 7919 * rank)
-    x = sla.SpVector.generate(n, SEED_CFG2 + 1)
-    y = sla.SpVector.zeroSV(n)
-    nbytes = A.spmv_bytes
-    for _ in range(args.warmup):
-        A.matVec(x, out=y)
-    barrier()
+    nbytes = spmv_bytes(n, n * k)                         # algorithmic bytes of the GLOBAL product
+    A = gen(sla.GEN_UNIFORM, n, k, SEED_CFG2)
+    starts = A.row_starts
+    nloc = starts[rank + 1] - starts[rank]
+    x = vec(n, SEED_CFG2 + 1, starts)
+    y = sla.SpVector.zeroSV(nloc)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launches
-    ctx.timer_start()
-    for _ in range(args.steps):
-        A.matVec(x, out=y)
-    ms = ctx.timer_stop()
-    barrier()
-    launches = ctx.launches - l0
-    ms = max_over_ranks(ms)
-    ms_per_step = ms / args.steps
-    value = world * nbytes / (ms_per_step * 1e-3) / 1e9
-    kernel_gbs = nbytes / (ms_per_step * 1e-3) / 1e9          # one launch per step: the SpMV kernel itself
+    ms_per_step, launches = timed(lambda: A.matVec(x, out=y), args.steps, args.warmup)
+    value = nbytes / (ms_per_step * 1e-3) / 1e9
+    kernel_gbs = value / world                             # per-GPU share of the algorithmic bytes
 
-    # ---- e2e: host buffers through sla_spmv_host (pinned x -> device, kernel, device y -> host)
-    xh = ctx.pinned(n)
-    yh = ctx.pinned(n)
-    xh[:] = x.toDenseListSV()
+    # ---- e2e: host buffers through sla_spmv_host (pinned x slice -> device, exchange + kernel, y slice -> host)
     import ctypes as C
 
+    xh = ctx.pinned(max(nloc, 1))
+    yh = ctx.pinned(max(nloc, 1))
+    xh[:nloc] = x.toDenseListSV()
     pd = C.POINTER(C.c_double)
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
+
+    def e2e_call():
         ctx.check(ctx.lib.sla_spmv_host(ctx.h, A.h, xh.ctypes.data_as(pd), yh.ctypes.data_as(pd)))
+
+    for _ in range(2):
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.check(ctx.lib.sla_spmv_host(ctx.h, A.h, xh.ctypes.data_as(pd), yh.ctypes.data_as(pd)))
+        e2e_call()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-    e2e_gbs = world * nbytes / e2e_s / 1e9
+    e2e_gbs = nbytes / e2e_s / 1e9
     clocks = sampler.stop() if rank == 0 else None
+    exchange = getattr(A, "dist_plan", [])
+    recv_bytes = 8 * sum(c for d, _, _, c in exchange if d == 0)
 
-    # ---- banded variant of config 2 (columns within +-65536 of the row) for context
-    extra = {}
-    if world == 1 and not args.quick:
+    extra = {"x_exchange_recv_bytes_per_rank": recv_bytes}
+    if not args.quick:
         del A
-        B = sla.SpMatrix.generate(sla.GEN_BANDED, n, k, SEED_CFG2, 65536)
-        for _ in range(args.warmup):
-            B.matVec(x, out=y)
-        ctx.timer_start()
-        for _ in range(args.steps):
-            B.matVec(x, out=y)
-        msb = ctx.timer_stop() / args.steps
-        extra["spmv_banded_gbs"] = B.spmv_bytes / (msb * 1e-3) / 1e9
+        # ---- banded variant of config 2 (columns within +-65536 of the row)
+        B = gen(sla.GEN_BANDED, n, k, SEED_CFG2, 65536)
+        msb, _ = timed(lambda: B.matVec(x, out=y), args.steps, args.warmup)
+        extra["spmv_banded_gbs"] = nbytes / (msb * 1e-3) / 1e9
         extra["spmv_banded_ms"] = msb
         del B
         # ---- config 3: BiCGSTAB on the 5-point Laplacian 4096^2, fixed number of bicgstabStep calls
         g = G_CFG3
         n3 = g * g
-        L3 = sla.SpMatrix.generate(sla.GEN_LAPLACE2D, n3, 5, 0, g)
-        xt = sla.SpVector.generate(n3, 3)
+        L3 = gen(sla.GEN_LAPLACE2D, n3, 5, 0, g)
+        s3 = L3.row_starts
+        n3loc = s3[rank + 1] - s3[rank]
+        xt = vec(n3, 3, s3)
         b = L3 @ xt
-        st = sla.bicgsInit(L3, b, sla.SpVector.zeroSV(n3))
+        st = sla.bicgsInit(L3, b, sla.SpVector.zeroSV(n3loc))
         rhat = st.r.copy()
         its = max(10, min(args.steps, 100))
-        for _ in range(5):
-            sla.bicgstabStep(L3, rhat, st)
-        ctx.sync()
-        ctx.timer_start()
-        for _ in range(its):
-            sla.bicgstabStep(L3, rhat, st)
-        ms3 = ctx.timer_stop() / its
-        b3 = 24 * L3.nnz + 168 * n3                       # B_bicgstab_step, SURVEY.md §8(d)
+        ms3, l3 = timed(lambda: sla.bicgstabStep(L3, rhat, st), its, 5)
+        nnz3 = 5 * n3 - 4 * g
+        b3 = 24 * nnz3 + 168 * n3                          # B_bicgstab_step, SURVEY.md §8(d)
         extra["bicgstab_cfg3_iters_per_s"] = 1e3 / ms3
         extra["bicgstab_cfg3_ms_per_iter"] = ms3
         extra["bicgstab_cfg3_gbs"] = b3 / (ms3 * 1e-3) / 1e9
-        ctx.timer_start()
-        for _ in range(its):
-            L3.matVec(xt, out=b)
-        ms3s = ctx.timer_stop() / its
-        extra["spmv_cfg3_gbs"] = L3.spmv_bytes / (ms3s * 1e-3) / 1e9
+        extra["bicgstab_cfg3_launches_per_iter"] = l3 / its
+        ms3s, _ = timed(lambda: L3.matVec(xt, out=b), its, 3)
+        extra["spmv_cfg3_gbs"] = spmv_bytes(n3, nnz3) / (ms3s * 1e-3) / 1e9
         del L3, st
 
     if rank != 0:
@@ -264,7 +278,7 @@ def run_gpu(args):
     peak, peak_src = load_peak()
     for key in ("spmv_banded_gbs", "bicgstab_cfg3_gbs", "spmv_cfg3_gbs"):
         if key in extra:
-            extra[key.replace("_gbs", "_frac")] = extra[key] / peak
+            extra[key.replace("_gbs", "_frac_per_gpu")] = extra[key] / world / peak
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -273,15 +287,17 @@ def run_gpu(args):
                "seconds_per_matvec_on_sample": sec}
     out = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: CSR SpMV (#>) fp64, 10M x 10M, 32 nnz/row, uniform columns, 1 x B200 per rank",
+        "config": {"workload": "cfg2: CSR SpMV (#>) fp64, 10M x 10M, 32 nnz/row, uniform columns"
+                               + (f", row-partitioned over {world} B200 (x all-gathered every step)" if world > 1 else ", 1 x B200"),
                    "n": n, "nnz": n * k, "algorithmic_bytes_per_step": nbytes,
                    "l2": "no flush: the 3.84 GB matrix stream exceeds the 126 MB L2 every step"},
         "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
-                     "traffic": load_traffic(), "peak_source": peak_src, "kernel": "spmv_tile_kernel<2048, EPI_NONE>"},
-        "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                "ms_per_step": e2e_s * 1e3, "api": "sla_spmv_host (pinned host buffers)"},
+                     "traffic": load_traffic(), "peak_source": peak_src, "per_gpu": True,
+                     "kernel": "spmv_tile_kernel<2048, EPI_NONE> (one launch per column panel, 2 panels at n = 10M)"},
+        "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8 * nloc, "d2h_bytes_per_step": 8 * nloc,
+                "ms_per_step": e2e_s * 1e3, "api": "sla_spmv_host (pinned host buffers, per-rank slices)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "cpu_baseline": cpu,

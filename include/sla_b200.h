@@ -89,7 +89,7 @@ sla_status sla_csr_generate_rows(sla_ctx*, int kind, int64_t n, int nnz_per_row,
                                  int64_t row_lo, int64_t row_hi, sla_csr** out);
 sla_status sla_csr_col_range(sla_ctx*, const sla_csr*, int64_t* lo, int64_t* hi);   /* hi < lo: no entries */
 sla_status sla_csr_set_dist(sla_ctx*, sla_csr*, int64_t row0, int nseg, const int* dir, const int* peer,
-                            const int64_t* goff, const int64_t* count);
+                            const int64_t* goff, const int64_t* count, int allgather /* same value on EVERY rank */);
 sla_status sla_vec_generate_slice(sla_ctx*, int64_t i0, int64_t n, uint64_t seed, sla_vec** out);
 sla_status sla_csr_dims(const sla_csr*, int64_t* m, int64_t* n, int64_t* nnz);
 sla_status sla_csr_to_host(sla_ctx*, const sla_csr*, int32_t* row_ptr, int32_t* col_idx, double* val);

@@ -133,7 +133,7 @@ void sla_csr_free_dist(sla_csr* A) {
 // which contiguous pieces of x travel (dir 0: receive [goff, goff+count) of the global vector from peer;
 // dir 1: send local entries [goff - row0, ...) to peer).  The plan is computed on the host (dist.py).
 extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int nseg, const int* dir, const int* peer,
-                                       const int64_t* goff, const int64_t* count) {
+                                       const int64_t* goff, const int64_t* count, int allgather) {
   if (!c || !A || nseg < 0 || (nseg > 0 && (!dir || !peer || !goff || !count))) return SLA_ERR_INVALID;
   if (row0 < 0 || row0 + A->m > A->n) return sla_fail(c, SLA_ERR_INVALID, "set_dist: local row block lies outside the global index range");
   sla_csr_free_dist(A);
@@ -154,12 +154,14 @@ extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int
     return sla_fail(c, SLA_ERR_ALLOC, "set_dist: cudaMalloc failed for the gathered x buffer");
   }
   cudaMemsetAsync(d->xfull, 0, sizeof(double) * (size_t)A->n, c->stream);
-  // uniform partition + every peer sends its whole block to everybody = an all-gather
-  if (c->world > 1 && A->n % c->world == 0 && A->m == A->n / c->world && row0 == (int64_t)c->rank * A->m) {
-    int full = 0;
-    for (int s = 0; s < nseg; ++s)
-      if (d->seg[s].dir == 0 && d->seg[s].count == A->m && d->seg[s].goff == (int64_t)d->seg[s].peer * A->m) ++full;
-    if (full == c->world - 1) d->allgather = 1;
+  // allgather is a COLLECTIVE decision taken by the host planner from the global needs table (every rank must
+  // issue the same NCCL call); it requires equal blocks laid out in rank order.
+  if (allgather) {
+    if (c->world < 2 || A->n % c->world != 0 || A->m != A->n / c->world || row0 != (int64_t)c->rank * A->m) {
+      cudaFree(d->xfull); delete[] d->seg; delete d;
+      return sla_fail(c, SLA_ERR_INVALID, "set_dist: all-gather needs equal row blocks in rank order");
+    }
+    d->allgather = 1;
   }
   A->dist = d;
   return SLA_OK;

@@ -55,6 +55,29 @@ def plan_exchange(rank, starts, needs):
     return segs
 
 
+def densify_needs(starts, needs):
+    """Collective decision, identical on every rank because it only looks at the global tables: when the exact
+    (halo) plan would already move more than half of every rank's remote entries, treat the column support as
+    dense (each rank receives every other block whole).  Returns (needs, use_allgather); all-gather additionally
+    needs equal blocks, because every rank must then issue the same NCCL collective.  (Deciding this per rank
+    deadlocks: a rank whose rows happen not to touch column 0 would issue send/recv against its peers'
+    all-gather.)"""
+    world, n = len(starts) - 1, starts[-1]
+
+    def halo_volume(q):      # entries rank q would receive under the exact (halo) plan
+        lo, hi = needs[q]
+        if hi < lo:
+            return 0
+        return sum((_overlap(lo, hi, starts[p], starts[p + 1]) or (0, 0))[1] for p in range(world) if p != q)
+
+    live = [q for q in range(world) if needs[q][1] >= needs[q][0]]
+    dense = bool(live) and all(2 * halo_volume(q) > n - (starts[q + 1] - starts[q]) for q in live)
+    if not dense:
+        return list(needs), False
+    equal = n % world == 0 and all(starts[p] == p * (n // world) for p in range(world + 1))
+    return [(0, n - 1)] * world, equal
+
+
 def exchange_bytes(segs):
     """(bytes received, bytes sent) per (#>) under this plan."""
     return (8 * sum(c for d, _, _, c in segs if d == 0), 8 * sum(c for d, _, _, c in segs if d == 1))
@@ -85,13 +108,13 @@ def init_context(device=None):
     return ctx
 
 
-def _install_plan(ctx, A, row0, segs):
+def _install_plan(ctx, A, row0, segs, allgather=False):
     n = len(segs)
     dirs = (C.c_int * max(n, 1))(*[s[0] for s in segs])
     peers = (C.c_int * max(n, 1))(*[s[1] for s in segs])
     goff = (C.c_int64 * max(n, 1))(*[s[2] for s in segs])
     cnt = (C.c_int64 * max(n, 1))(*[s[3] for s in segs])
-    ctx.check(ctx.lib.sla_csr_set_dist(ctx.h, A.h, row0, n, dirs, peers, goff, cnt))
+    ctx.check(ctx.lib.sla_csr_set_dist(ctx.h, A.h, row0, n, dirs, peers, goff, cnt, 1 if allgather else 0))
 
 
 def distribute(ctx, A, starts):
@@ -104,9 +127,11 @@ def distribute(ctx, A, starts):
     ctx.check(ctx.lib.sla_csr_col_range(ctx.h, A.h, C.byref(lo), C.byref(hi)))
     needs = [None] * world
     dist.all_gather_object(needs, (lo.value, hi.value))
+    needs, allgather = densify_needs(starts, needs)
     segs = plan_exchange(rank, starts, needs)
-    _install_plan(ctx, A, starts[rank], segs)
+    _install_plan(ctx, A, starts[rank], segs, allgather)
     A.dist_plan = segs
+    A.dist_allgather = allgather
     A.row_starts = starts
     return A
 

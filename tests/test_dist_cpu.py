@@ -10,7 +10,7 @@ import pytest
 
 
 def test_row_partition_and_plan_unit():
-    from sparse_linear_algebra_b200.dist import exchange_bytes, plan_exchange, row_partition
+    from sparse_linear_algebra_b200.dist import densify_needs, exchange_bytes, plan_exchange, row_partition
 
     assert row_partition(10, 3) == [0, 3, 6, 10]
     assert row_partition(7, 1) == [0, 7]
@@ -30,6 +30,14 @@ def test_row_partition_and_plan_unit():
     pl = plan_exchange(2, starts, needs)
     assert sorted(s for s in pl if s[0] == 0) == [(0, 0, 0, 25), (0, 1, 25, 25), (0, 3, 75, 25)]
     assert sorted(s for s in pl if s[0] == 1) == [(1, 0, 50, 25), (1, 1, 50, 25), (1, 3, 50, 25)]
+    # the all-gather decision is collective: taken from the global table, so it is the same on every rank even
+    # when one rank happens not to touch the first / last column
+    starts8 = row_partition(800, 8)
+    needs8 = [(0, 799)] * 7 + [(3, 790)]
+    nd, ag = densify_needs(starts8, needs8)
+    assert ag and nd == [(0, 799)] * 8
+    assert densify_needs(row_partition(801, 8), [(0, 800)] * 8) == ([(0, 800)] * 8, False)      # ragged: p2p, full blocks
+    assert densify_needs(starts8, [(max(0, s - 5), s + 104) for s in starts8[:-1]])[1] is False  # banded stays a halo plan
     # an empty block neither receives nor is sent anything on its behalf
     needs = [(0, 99), (0, -1), (0, 99), (0, 99)]
     assert all(s[0] == 1 for s in plan_exchange(1, starts, needs))
@@ -50,7 +58,7 @@ def _worker(rank, world, port, kind_name, n, k, band, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import oracle as ora
-        from sparse_linear_algebra_b200.dist import plan_exchange, row_partition
+        from sparse_linear_algebra_b200.dist import densify_needs, plan_exchange, row_partition
 
         kind = getattr(ora, kind_name)
         seed = 0x5EED0005
@@ -64,6 +72,7 @@ def _worker(rank, world, port, kind_name, n, k, band, ret):
         need = (int(col.min()), int(col.max())) if col.size else (0, -1)
         needs = [None] * world
         dist.all_gather_object(needs, need)
+        needs, _ = densify_needs(starts, needs)
         segs = plan_exchange(rank, starts, needs)
         # execute the plan with gloo point-to-point copies
         x_local = ora.SpVector.synth(seed + 1, n).toDenseListSV()[r0:r1].copy()
