@@ -159,6 +159,16 @@ sla_status sla_arnoldi(sla_ctx*, const sla_csr* A, const sla_vec* b, int kn, sla
 sla_status sla_gmres(sla_ctx*, const sla_csr* A, const sla_vec* b, const sla_vec* x0, int restart,
                      const sla_solve_opts*, sla_vec* x, int* iters, double* resnorm);
 
+/* ---- (##) with a dense right operand  (matMat_ AB, SpMatrix.hs:768-811) ---------------------
+ * B (n x k) and C (m x k) are ROW-major dense blocks.  SLA_F64: products rounded once and summed in ascending
+ * column order — bit-identical to the reference.  SLA_BF16: A values and B in bf16, fp32 accumulation, C bf16
+ * (BASELINE config 5). */
+typedef enum { SLA_F64 = 0, SLA_BF16 = 1 } sla_dtype;
+sla_status sla_dense_create(sla_ctx*, int64_t rows, int64_t cols, int dtype, sla_dense** out);
+sla_status sla_dense_from_host(sla_ctx*, int64_t rows, int64_t cols, const double* rowmajor, int dtype, sla_dense** out);
+sla_status sla_dense_to_host_f64(sla_ctx*, const sla_dense*, double* rowmajor_out);
+sla_status sla_spmm_dense(sla_ctx*, const sla_csr* A, const sla_dense* B, sla_dense* C);
+
 /* ---- dense blocks -------------------------------------------------------------------------- */
 sla_status sla_dense_dims(const sla_dense*, int64_t* rows, int64_t* cols);
 sla_status sla_dense_to_host(sla_ctx*, const sla_dense*, double* out_colmajor);

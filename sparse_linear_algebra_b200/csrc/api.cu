@@ -324,6 +324,7 @@ extern "C" sla_status sla_dense_dims(const sla_dense* d, int64_t* rows, int64_t*
 
 extern "C" sla_status sla_dense_to_host(sla_ctx* c, const sla_dense* d, double* out) {
   if (!c || !d || !out) return SLA_ERR_INVALID;
+  if (d->rowmajor) return sla_fail(c, SLA_ERR_INVALID, "dense_to_host: block is row-major (use sla_dense_to_host_f64)");
   SLA_CUDA(c, cudaMemcpy2DAsync(out, sizeof(double) * (size_t)d->rows, d->d, sizeof(double) * (size_t)d->ld,
                                 sizeof(double) * (size_t)d->rows, (size_t)d->cols, cudaMemcpyDeviceToHost, c->stream));
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));

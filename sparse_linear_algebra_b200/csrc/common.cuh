@@ -76,6 +76,7 @@ struct sla_csr {
   int npanels;               // >= 2 when the column-panel copy exists
   sla_panel* panels;         // host array of device pointers
   sla_dist_info* dist;       // non-null: this is the local row block of a distributed matrix (n = GLOBAL columns)
+  void* val_bf16;            // bf16 copy of val for the bf16 (##) path, built on first use (spmm.cu)
 };
 
 // dimension a vector must have to be multiplied by A / to receive A's product, on this rank
@@ -83,7 +84,8 @@ static inline int64_t csr_xdim(const sla_csr* A) { return A->dist ? A->m : A->n;
 
 struct sla_dense {
   sla_ctx* ctx;
-  int64_t rows, cols, ld;    // column-major; ld = leading dimension (rows rounded up to 16 doubles)
+  int64_t rows, cols, ld;    // column-major (Krylov basis): ld = rows rounded up to 16 doubles; row-major (## operands): ld = cols
+  int dtype, rowmajor;       // SLA_F64 / SLA_BF16 ; 1 = row-major block created by sla_dense_create
   double* d;
 };
 

@@ -48,7 +48,7 @@ extern "C" void sla_csr_free(sla_csr* A) {
   if (A->T) sla_csr_free(A->T);
   sla_csr_free_panels(A);
   sla_csr_free_dist(A);
-  cudaFree(A->row_ptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->tile_row);
+  cudaFree(A->row_ptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->tile_row); cudaFree(A->val_bf16);
   delete A;
 }
 

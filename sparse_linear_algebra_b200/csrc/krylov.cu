@@ -399,6 +399,7 @@ static sla_status dense_alloc(sla_ctx* c, int64_t rows, int64_t cols, sla_dense*
   sla_dense* d = new (std::nothrow) sla_dense();
   if (!d) return sla_fail(c, SLA_ERR_ALLOC, "dense alloc");
   d->ctx = c; d->rows = rows; d->cols = cols; d->ld = (rows + 15) & ~(int64_t)15; d->d = nullptr;
+  d->dtype = SLA_F64; d->rowmajor = 0;
   if (d->ld == 0) d->ld = 16;
   if (cudaMalloc(&d->d, sizeof(double) * (size_t)d->ld * (size_t)(cols > 0 ? cols : 1)) != cudaSuccess) {
     cudaGetLastError(); delete d;

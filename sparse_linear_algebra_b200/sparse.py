@@ -292,6 +292,38 @@ class DenseBlock:
         return out.T.copy()
 
 
+F64, BF16 = 0, 1
+
+
+class DenseMatrix(DenseBlock):
+    """Row-major dense block: the dense right operand / result of (##) (fp64 or bf16)."""
+
+    def __init__(self, ctx, handle, dtype):
+        super().__init__(ctx, handle)
+        self.dtype = dtype
+
+    @staticmethod
+    def fromHost(a, dtype=F64, ctx=None):
+        ctx = ctx or default_context()
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.sla_dense_from_host(ctx.h, a.shape[0], a.shape[1], a.ctypes.data_as(C.POINTER(C.c_double)), dtype, C.byref(h)))
+        return DenseMatrix(ctx, h, dtype)
+
+    @staticmethod
+    def zeros(rows, cols, dtype=F64, ctx=None):
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        ctx.check(ctx.lib.sla_dense_create(ctx.h, rows, cols, dtype, C.byref(h)))
+        return DenseMatrix(ctx, h, dtype)
+
+    def toHost(self):
+        r, c = self.dim
+        out = np.zeros((r, c), dtype=np.float64)
+        self.ctx.check(self.ctx.lib.sla_dense_to_host_f64(self.ctx.h, self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+
 class SpMatrix:
     """SpMatrix Double on the device: CSR (row_ptr, col_idx ascending, val)."""
 
@@ -417,8 +449,13 @@ class SpMatrix:
         self.ctx.check(self.ctx.lib.sla_spmv_host(self.ctx.h, self.h, xp, y.ctypes.data_as(C.POINTER(C.c_double))))
         return y
 
+    def matMat(self, b, out=None):        # aa ## b, b a dense row-major block
+        cc = out if out is not None else DenseMatrix.zeros(self.nrows, b.dim[1], b.dtype, self.ctx)
+        self.ctx.check(self.ctx.lib.sla_spmm_dense(self.ctx.h, self.h, b.h, cc.h))
+        return cc
+
     def __matmul__(self, x):
-        return self.matVec(x)
+        return self.matMat(x) if isinstance(x, DenseMatrix) else self.matVec(x)
 
 
 class KrylovState:

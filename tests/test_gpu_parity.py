@@ -433,6 +433,64 @@ def test_gmres_converges(sla, o):
     np.testing.assert_allclose(x.toDenseListSV(), xt.toDenseListSV(), atol=1e-8)
 
 
+# =============================================================== (##) with a dense right operand
+
+def _bf16_round(a):
+    """Round-to-nearest-even to bfloat16, returned as float64."""
+    u = np.asarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+def test_ref_matmat_fixtures(sla):                       # LibSpec.hs:61-65, 1263-1271: exact ==
+    m1 = dense(sla, F.M1)
+    m2 = np.array([[5.0, 6.0], [7.0, 8.0]])
+    assert (m1 @ sla.DenseMatrix.fromHost(m2)).toHost().tolist() == [[19.0, 22.0], [43.0, 50.0]]
+    m1p = sla.SpMatrix.fromListSM(*F.M1P)                # [[2,0,0],[3,0,1]] after the duplicate overwrite
+    m2p = np.array([[5.0, 3.0], [0.0, 0.0], [0.0, 4.0]])
+    assert (m1p @ sla.DenseMatrix.fromHost(m2p)).toHost().tolist() == [[10.0, 6.0], [15.0, 13.0]]
+    with pytest.raises(sla.MatVecSizeMismatchException):  # error "matMat : incompatible matrix sizes"  SpMatrix.hs:790-797
+        m1 @ sla.DenseMatrix.fromHost(np.ones((3, 2)))
+
+
+@pytest.mark.parametrize("seed,m,n,k,nnz", [(40, 1, 1, 1, 1), (41, 70, 50, 7, 600), (42, 2000, 1500, 33, 30000), (43, 300, 4000, 128, 20000)])
+def test_spmm_f64_bit_exact(sla, o, seed, m, n, k, nnz):
+    """C_ic = sum_k asc b_kc * a_ik with the products rounded once: identical bits to the oracle's matMat_."""
+    rng = np.random.default_rng(seed)
+    i, j, v = _rand_coo(rng, m, n, nnz, long_rows=[(0, min(n, 400))] if n >= 400 else ())
+    A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+    Ao = o.SpMatrix.fromCOO((m, n), i, j, v)
+    B = rng.standard_normal((n, k))
+    C = (A @ sla.DenseMatrix.fromHost(B)).toHost()
+    Bo = o.SpMatrix.fromListDenseSM(n, B.T.reshape(-1))   # column-major list, every entry stored
+    Co = Ao.matMat(Bo).toDense()
+    assert C.tobytes() == Co.tobytes()
+
+
+def test_spmm_bf16_within_bound(sla, o):
+    """cfg 5 at reduced size: bf16 A values and B, fp32 accumulation, bf16 C, against the fp64 oracle on the
+    bf16-rounded inputs: |dC| <= 2^-8 |C| + (k_i + 2) 2^-24 sum|a||b|.  (bf16 keeps 8 significant bits, so the
+    final rounding is 2^-8 relative; SURVEY.md §8d wrote 2^-9.)"""
+    rng = np.random.default_rng(50)
+    m = n = 4096
+    k, nnz = 128, 32 * 4096
+    i, j = rng.integers(0, m, nnz), rng.integers(0, n, nnz)
+    v = _bf16_round(rng.uniform(-1, 1, nnz))
+    A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+    B = _bf16_round(rng.uniform(-1, 1, (n, k)))
+    C = (A @ sla.DenseMatrix.fromHost(B, sla.BF16)).toHost()
+    rp, ci, va = A.toCSR()
+    import scipy.sparse as sp
+
+    S = sp.csr_matrix((va, ci, rp), shape=(m, n))
+    Cref = S @ B
+    absum = abs(S) @ np.abs(B)
+    lens = np.diff(rp)[:, None]
+    bound = 2.0 ** -8 * np.abs(Cref) + (lens + 2) * 2.0 ** -24 * absum + 1e-30
+    assert np.all(np.abs(C - Cref) <= bound)
+    assert np.array_equal(C, _bf16_round(C))              # the output really is bf16
+
+
 # =============================================================== BASELINE sizes, size-independent properties
 
 def _seq_row_dot(cols, vals, x):
