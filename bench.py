@@ -130,7 +130,7 @@ def run_reference(args):
     sample = f"config-2 family (uniform, 32 nnz/row) at n={n_sample} rows per step; GB/s is size-normalised"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg2: CSR SpMV (#>) fp64, 10M x 10M, 32 nnz/row, uniform columns (bounded sample)",
                    "sample_rows": n_sample, "nnz_per_row": K_CFG2},
@@ -270,13 +270,28 @@ def run_gpu(args):
         ms3s, _ = timed(lambda: L3.matVec(xt, out=b), its, 3)
         extra["spmv_cfg3_gbs"] = spmv_bytes(n3, nnz3) / (ms3s * 1e-3) / 1e9
         del L3, st
+        # ---- config 4: arnoldi(A, b, 30) on the random non-symmetric 4M x 4M, 64 nnz/row matrix (row-partitioned)
+        n4, k4 = 4_000_000, 64
+        A4 = gen(sla.GEN_UNIFORM, n4, k4, 0x5EED0004)
+        b4 = vec(n4, 0x5EED0005, A4.row_starts)
+        sla.arnoldi(A4, b4, 4)                              # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        Qd, H4, brk4 = sla.arnoldi(A4, b4, 30)
+        barrier()
+        s4 = max_over_ranks(time.perf_counter() - t0)
+        b4bytes = 30 * spmv_bytes(n4, n4 * k4) + 8400 * n4    # B_arnoldi cycle, SURVEY.md §8(d)
+        extra["arnoldi_cfg4_steps_per_s"] = 30 / s4
+        extra["arnoldi_cfg4_ms_per_cycle"] = s4 * 1e3
+        extra["arnoldi_cfg4_gbs"] = b4bytes / s4 / 1e9
+        del A4, Qd
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     peak, peak_src = load_peak()
-    for key in ("spmv_banded_gbs", "bicgstab_cfg3_gbs", "spmv_cfg3_gbs"):
+    for key in ("spmv_banded_gbs", "bicgstab_cfg3_gbs", "spmv_cfg3_gbs", "arnoldi_cfg4_gbs"):
         if key in extra:
             extra[key.replace("_gbs", "_frac_per_gpu")] = extra[key] / world / peak
     cpu = None

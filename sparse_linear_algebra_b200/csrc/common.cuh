@@ -12,6 +12,7 @@
 #define SLA_SCAL_SLOTS 1024      // device scalar slots per ctx
 #define SLA_MAX_KRYLOV 384       // max Arnoldi / GMRES basis size (H column lives in scal[S_HCOL..])
 #define SLA_MAX_PARTIALS (1 << 20)
+#define SLA_MAX_PANELS 64        // column panels per matrix (spmv.cu)
 
 // device scalar slots (doubles living in ctx->scal)
 enum {
@@ -31,6 +32,10 @@ struct sla_ctx {
   double* h_scal;            // pinned host mirror for scalar read-back
   int64_t launches;
   void* nccl;                // ncclComm_t when world > 1
+  void* nccl_x;              // second communicator (ncclCommSplit) for the x exchange on comm_stream
+  cudaStream_t comm_stream;  // the x exchange runs here so that it overlaps the column-panel kernels
+  cudaEvent_t ev_x0;         // "x is ready / xfull may be overwritten" (compute -> comm)
+  cudaEvent_t ev_panel[SLA_MAX_PANELS];   // "panel p of xfull has arrived" (comm -> compute)
   struct sla_vec *scratch_x, *scratch_y;   // device staging for the host-pointer entry points
   struct sla_vec* scratch_r;               // partial row sums of the panelised residual-norm SpMV
   int spmv_hints;            // bit0: matrix stream L2 evict_first, bit1: x gathers L2 evict_last (env SLA_SPMV_HINTS)
@@ -58,7 +63,12 @@ struct sla_dist_info {
   int64_t row0;              // global index of the first local row (= first entry of the local x slice)
   int nseg; sla_xseg* seg;
   double* xfull;             // n doubles; only the remote entries this rank references are kept current
-  int allgather;             // the plan is a plain all-gather of equal slices
+  int allgather;             // the plan is a plain all-gather of equal slices (collective decision)
+  // dense plans are pipelined: the segments clipped to each column panel, exchanged panel by panel on
+  // comm_stream while the kernels of the earlier panels run
+  int pipelined;
+  int pan_first[SLA_MAX_PANELS + 1];   // pseg[pan_first[p] .. pan_first[p+1]) belong to panel p
+  sla_xseg* pseg;
 };
 
 struct sla_csr {
@@ -74,6 +84,7 @@ struct sla_csr {
   int skew_a;                // shared-memory skew shift of the SpMV product buffer (spmv.cu)
   int hints;                 // cache-hint bits of the SpMV loads chosen by the plan (spmv.cu)
   int npanels;               // >= 2 when the column-panel copy exists
+  int panel_width;           // columns per panel
   sla_panel* panels;         // host array of device pointers
   sla_dist_info* dist;       // non-null: this is the local row block of a distributed matrix (n = GLOBAL columns)
   void* val_bf16;            // bf16 copy of val for the bf16 (##) path, built on first use (spmm.cu)
@@ -256,6 +267,8 @@ sla_status sla_read_scalars(sla_ctx* c, int first, int count, double* host_out);
 // multi-GPU (dist.cu)
 sla_status sla_dist_finish_reduction(sla_ctx* c, int nv, int fin, int dst);
 sla_status sla_dist_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local);
+sla_status sla_dist_exchange_panel(sla_ctx* c, const sla_csr* A, const double* x_local, int p);   // on comm_stream
+sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P);                                   // spmv.cu
 sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count);
 void sla_csr_free_dist(sla_csr* A);
 static inline int fin_for(const sla_ctx* c, int fin) { return c->world > 1 ? (fin | FIN_DEFER) : fin; }

@@ -18,6 +18,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*);   // optional (NCCL >= 2.18)
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
@@ -39,6 +40,7 @@ static bool nccl_bind() {
   BIND(AllReduce, "ncclAllReduce"); BIND(AllGather, "ncclAllGather"); BIND(Send, "ncclSend"); BIND(Recv, "ncclRecv");
   BIND(GroupStart, "ncclGroupStart"); BIND(GroupEnd, "ncclGroupEnd"); BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
+  *(void**)(&g_nccl.CommSplit) = dlsym(h, "ncclCommSplit");
   g_nccl.ok = true;
   return true;
 }
@@ -82,10 +84,28 @@ sla_status sla_dist_attach(sla_ctx* c, const void* nccl_id128) {
   SLA_CUDA(c, cudaSetDevice(c->device));
   SLA_NCCL(c, ncclCommInitRank(&comm, c->world, id, c->rank));
   c->nccl = (void*)comm;
+  // the x exchange gets its own stream and, when the library offers it, its own communicator, so that it can
+  // run under the column-panel kernels without being serialised behind the all-reduces of the compute stream
+  c->nccl_x = c->nccl;
+  if (g_nccl.CommSplit) {
+    ncclComm_t cx = nullptr;
+    if (g_nccl.CommSplit(comm, 0, c->rank, &cx, nullptr) == ncclSuccess && cx) c->nccl_x = (void*)cx;
+  }
+  SLA_CUDA(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  SLA_CUDA(c, cudaEventCreateWithFlags(&c->ev_x0, cudaEventDisableTiming));
+  for (int p = 0; p < SLA_MAX_PANELS; ++p) SLA_CUDA(c, cudaEventCreateWithFlags(&c->ev_panel[p], cudaEventDisableTiming));
   return SLA_OK;
 }
 
 void sla_dist_detach(sla_ctx* c) {
+  if (c->comm_stream) {
+    cudaStreamSynchronize(c->comm_stream);
+    cudaStreamDestroy(c->comm_stream); c->comm_stream = nullptr;
+    cudaEventDestroy(c->ev_x0);
+    for (int p = 0; p < SLA_MAX_PANELS; ++p) cudaEventDestroy(c->ev_panel[p]);
+  }
+  if (c->nccl_x && c->nccl_x != c->nccl) ncclCommDestroy((ncclComm_t)c->nccl_x);
+  c->nccl_x = nullptr;
   if (c->nccl) { ncclCommDestroy((ncclComm_t)c->nccl); c->nccl = nullptr; }
 }
 
@@ -123,8 +143,10 @@ sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count) {
 
 void sla_csr_free_dist(sla_csr* A) {
   if (!A->dist) return;
+  if (A->ctx && A->ctx->comm_stream) cudaStreamSynchronize(A->ctx->comm_stream);
   cudaFree(A->dist->xfull);
   delete[] A->dist->seg;
+  delete[] A->dist->pseg;
   delete A->dist;
   A->dist = nullptr;
 }
@@ -139,7 +161,7 @@ extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int
   sla_csr_free_dist(A);
   sla_dist_info* d = new (std::nothrow) sla_dist_info();
   if (!d) return sla_fail(c, SLA_ERR_ALLOC, "set_dist alloc");
-  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0;
+  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0; d->pipelined = 0; d->pseg = nullptr;
   d->seg = new sla_xseg[nseg > 0 ? nseg : 1];
   for (int s = 0; s < nseg; ++s) {
     if (peer[s] < 0 || peer[s] >= c->world || peer[s] == c->rank || goff[s] < 0 || count[s] < 0 || goff[s] + count[s] > A->n ||
@@ -164,6 +186,59 @@ extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int
     d->allgather = 1;
   }
   A->dist = d;
+  // EXPERIMENTAL (SLA_DIST_PIPELINE=1): pipeline the exchange under the column-panel kernels.  The panel count is
+  // derived from global quantities only (n), so every rank clips the same segments at the same boundaries.
+  // Measured on B200 (cfg 2, round 1): the grouped ncclSend/ncclRecv per panel are slower than one ncclAllGather
+  // (N=2: 0.994 vs 0.950 ms, N=4: 0.694 vs 0.566 ms) and only the exchange of the panels after the first can hide
+  // behind compute, so the default stays the single all-gather; see DESIGN.md §5.
+  if (allgather && c->world > 1 && getenv("SLA_DIST_PIPELINE")) {
+    int P = (int)(((uint64_t)A->n * 8u + (40u << 20) - 1) / (40u << 20));
+    if (P < 2) P = 2;
+    if (const char* e = getenv("SLA_DIST_PANELS")) P = atoi(e);
+    if ((uint64_t)A->n * 8u >= (4u << 20) && P >= 2) {
+      sla_status ps = sla_csr_force_panels(c, A, P);
+      if (ps != SLA_OK) { sla_csr_free_dist(A); return ps; }
+      const int np = A->npanels;
+      const int64_t W = A->panel_width;
+      // clip every segment to every panel it overlaps
+      int total = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        int k = 0;
+        for (int p = 0; p < np; ++p) {
+          if (pass == 1) d->pan_first[p] = k;
+          const int64_t lo = (int64_t)p * W, hi = lo + W < A->n ? lo + W : A->n;
+          for (int sgi = 0; sgi < nseg; ++sgi) {
+            const sla_xseg& g = d->seg[sgi];
+            const int64_t a = g.goff > lo ? g.goff : lo, b = g.goff + g.count < hi ? g.goff + g.count : hi;
+            if (b <= a) continue;
+            if (pass == 1) { d->pseg[k].dir = g.dir; d->pseg[k].peer = g.peer; d->pseg[k].goff = a; d->pseg[k].count = b - a; }
+            ++k;
+          }
+        }
+        if (pass == 0) { total = k; d->pseg = new sla_xseg[total > 0 ? total : 1]; }
+        else d->pan_first[np] = k;
+      }
+      d->pipelined = 1;
+      d->allgather = 0;      // the per-panel point-to-point groups replace the single all-gather
+    }
+  }
+  A->dist = d;
+  return SLA_OK;
+}
+
+// the exchange restricted to column panel p, issued on comm_stream (the caller orders it with events)
+sla_status sla_dist_exchange_panel(sla_ctx* c, const sla_csr* A, const double* x_local, int p) {
+  const sla_dist_info* d = A->dist;
+  ncclComm_t comm = (ncclComm_t)c->nccl_x;
+  const int s0 = d->pan_first[p], s1 = d->pan_first[p + 1];
+  if (s1 <= s0) return SLA_OK;
+  SLA_NCCL(c, ncclGroupStart());
+  for (int s = s0; s < s1; ++s) {
+    const sla_xseg& g = d->pseg[s];
+    if (g.dir == 0) SLA_NCCL(c, ncclRecv(d->xfull + g.goff, (size_t)g.count, ncclDouble, g.peer, comm, c->comm_stream));
+    else            SLA_NCCL(c, ncclSend(x_local + (g.goff - d->row0), (size_t)g.count, ncclDouble, g.peer, comm, c->comm_stream));
+  }
+  SLA_NCCL(c, ncclGroupEnd());
   return SLA_OK;
 }
 

@@ -145,7 +145,7 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
   double e0 = 0.0, e1 = 0.0;
   for (int j = tid; j < nrows; j += SPMV_THREADS) {
     const int r = row_lo + j;
-    const int s = row_ptr[r], e = row_ptr[r + 1];
+    const int s = row_ptr[r], e = row_ptr[r + 1];   // (requesting these before phase 1 was measured slower: 1.76 vs 1.49 ms on cfg 2)
     if (e - s > SLA_LONG_ROW) {
       const int slot = atomicAdd(&n_long, 1);
       long_rows[slot] = r;
@@ -328,6 +328,8 @@ static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
   void* tmp = nullptr;
   A->panels = new sla_panel[P]();
   A->npanels = P;
+  A->panel_width = width;
+  if (m == 0) return SLA_OK;          // a rank without rows still takes part in the per-panel exchange
   sla_status s = SLA_OK;
   do {
     if (cudaMalloc(&start, sizeof(int) * (size_t)P * m) != cudaSuccess || cudaMalloc(&len, sizeof(int) * (size_t)P * m) != cudaSuccess ||
@@ -410,8 +412,20 @@ sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
     if ((uint64_t)A->n * 8u <= SLA_PANEL_MIN_X || mean_span_bytes <= (double)SLA_PANEL_MIN_SPAN) return SLA_OK;
     want = (int)(((uint64_t)A->n * 8u + SLA_PANEL_BYTES - 1) / SLA_PANEL_BYTES);
   }
-  if (want > 64) want = 64;
+  if (want > SLA_MAX_PANELS) want = SLA_MAX_PANELS;
   return build_panels(c, A, want);
+}
+
+// Multi-GPU: the panel count of a densely-coupled distributed matrix is a collective choice (every rank clips
+// the same exchange segments with the same panel boundaries), so dist.cu imposes it here.
+sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P) {
+  if (P > SLA_MAX_PANELS) P = SLA_MAX_PANELS;
+  int width = (int)((A->n + P - 1) / P);
+  width = (width + 15) & ~15;
+  if (A->npanels >= 2 && A->panel_width == width) return SLA_OK;
+  sla_csr_free_panels(A);
+  if (P < 2) return SLA_OK;
+  return build_panels(c, A, P);
 }
 
 // Sums the two per-CTA partial arrays of an SpMV epilogue in a fixed order (thread-strided sequential, then the
@@ -487,7 +501,18 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   (void)u1;
   if (A->ntiles > SLA_MAX_PARTIALS) return sla_fail(c, SLA_ERR_INVALID, "spmv: matrix has too many tiles");
   const bool dist = A->dist != nullptr;
-  if (dist) SLA_TRY(sla_dist_exchange_x(c, A, x));          // every rank takes part, even with no local rows
+  // Dense multi-GPU plans are pipelined: the exchange of panel p+1 (comm stream) overlaps the kernel of panel p.
+  const bool pipelined = dist && A->dist->pipelined && A->npanels >= 2 && c->world > 1;
+  if (pipelined) {
+    SLA_CUDA(c, cudaEventRecord(c->ev_x0, c->stream));                  // x is final, earlier readers of xfull are done
+    SLA_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_x0, 0));
+    for (int p = 0; p < A->npanels; ++p) {
+      SLA_TRY(sla_dist_exchange_panel(c, A, x, p));
+      SLA_CUDA(c, cudaEventRecord(c->ev_panel[p], c->comm_stream));
+    }
+  } else if (dist) {
+    SLA_TRY(sla_dist_exchange_x(c, A, x));                              // every rank takes part, even with no local rows
+  }
   SpmvArgs a;
   a.row_ptr = A->row_ptr; a.col = A->col; a.val = A->val; a.tile_row = A->tile_row;
   a.ntiles = A->ntiles; a.skew_a = A->skew_a; a.hints = A->hints;
@@ -509,6 +534,16 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
     a.row_ptr = pn.row_ptr; a.col = pn.col; a.val = pn.val; a.tile_row = pn.tile_row;
     a.ntiles = pn.ntiles; a.skew_a = pn.skew_a;
     a.yin = p == 0 ? nullptr : ybuf; a.y = ybuf;
+    if (pipelined) SLA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_panel[p], 0));
+    if (A->m == 0) {
+      // a rank without rows has no panel arrays; it still joins the epilogue's all-reduce through the (empty) base plan
+      if (last) {
+        a.row_ptr = A->row_ptr; a.col = A->col; a.val = A->val; a.tile_row = A->tile_row; a.ntiles = A->ntiles; a.skew_a = A->skew_a;
+        a.yin = nullptr;
+        SLA_TRY(launch_any(c, epi, false, dist, a));
+      }
+      continue;
+    }
     SLA_TRY(launch_any(c, last ? epi : EPI_NONE, p > 0, dist, a));
   }
   return SLA_OK;
