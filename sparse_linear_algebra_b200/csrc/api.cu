@@ -34,6 +34,7 @@ static sla_status ctx_create(int device, int rank, int world, sla_ctx** out) {
   c->device = device; c->rank = rank; c->world = world;
   c->spmv_hints = 3;
   if (const char* h = getenv("SLA_SPMV_HINTS")) c->spmv_hints = atoi(h);
+  if (const char* h = getenv("SLA_SPMV_TMA")) c->spmv_tma = atoi(h);
   SLA_CUDA(c, cudaSetDevice(device));
   SLA_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   SLA_CUDA(c, cudaEventCreate(&c->ev0));

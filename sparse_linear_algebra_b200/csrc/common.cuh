@@ -39,6 +39,7 @@ struct sla_ctx {
   struct sla_vec *scratch_x, *scratch_y;   // device staging for the host-pointer entry points
   struct sla_vec* scratch_r;               // partial row sums of the panelised residual-norm SpMV
   int spmv_hints;            // bit0: matrix stream L2 evict_first, bit1: x gathers L2 evict_last (env SLA_SPMV_HINTS)
+  int spmv_tma;              // 0: LDG tile kernel; k > 0: TMA-staged persistent kernel with k CTAs per SM (env SLA_SPMV_TMA)
   const void* scal_owner;    // Krylov state whose recurrence scalars currently live in scal[]
   char err[512];
 };

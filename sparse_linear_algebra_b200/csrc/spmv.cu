@@ -206,6 +206,180 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA variant: persistent CTAs, the (col, val) tile stream staged into shared memory by the bulk-copy engine
+// (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a ring of SPMV_STAGES buffers.  One elected
+// thread issues the copies for tile i + SPMV_STAGES as soon as tile i's stage has been consumed, so the
+// stream of the next tiles is in flight while the CTA gathers x, writes the products and sums its rows.
+// Arithmetic, ownership rule, epilogues and bit-exactness are those of spmv_tile_kernel.
+#define SPMV_STAGES 3
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+template <int TILE, int EPI, bool ACC, bool DIST>
+__global__ void __launch_bounds__(SPMV_THREADS)
+spmv_tma_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val,
+                const double* __restrict__ x, const double* yin, double* y, const int* __restrict__ tile_row,
+                const double* __restrict__ u0, double* partials, int ntiles, int hints,
+                const double* __restrict__ xr, int col0, int ncl) {
+  constexpr int PER = TILE / SPMV_THREADS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sval = reinterpret_cast<double*>(smem_raw);                                   // STAGES x TILE doubles
+  int* scol = reinterpret_cast<int*>(smem_raw + (size_t)SPMV_STAGES * TILE * 8);        // STAGES x TILE ints
+  double* prod = reinterpret_cast<double*>(smem_raw + (size_t)SPMV_STAGES * TILE * 12); // TILE + TILE/8 doubles
+  __shared__ uint64_t full_bar[SPMV_STAGES];
+  __shared__ double red[2 * 32];
+  __shared__ int long_rows[SLA_LONG_CAP];
+  __shared__ int n_long;
+
+  const int tid = threadIdx.x;
+  const int sk = hints >> 8;
+  const uint64_t pol_stream = (hints & 1) ? policy_evict_first() : policy_evict_normal();
+  const uint64_t pol_keep = (hints & 2) ? policy_evict_last() : policy_evict_normal();
+  if (tid == 0) {
+    for (int s = 0; s < SPMV_STAGES; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // make the inits visible to the async proxy
+  }
+  __syncthreads();
+
+  // prologue: fill the ring
+  if (tid == 0) {
+    for (int s = 0; s < SPMV_STAGES; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < ntiles) {
+        mbar_expect_tx(&full_bar[s], TILE * 12);
+        bulk_g2s(scol + s * TILE, col + (size_t)t * TILE, TILE * 4, &full_bar[s], pol_stream);
+        bulk_g2s(sval + s * TILE, val + (size_t)t * TILE, TILE * 8, &full_bar[s], pol_stream);
+      }
+    }
+  }
+
+  double e0 = 0.0, e1 = 0.0;
+  int it = 0;
+  int nxt_lo = 0, nxt_hi = 0;          // row range of the next tile, requested one iteration ahead
+  if ((int)blockIdx.x < ntiles) { nxt_lo = tile_row[blockIdx.x]; nxt_hi = tile_row[blockIdx.x + 1]; }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it % SPMV_STAGES;
+    const uint32_t parity = (uint32_t)((it / SPMV_STAGES) & 1);
+    const int base = tile * TILE;
+    const int row_lo = nxt_lo, row_hi = nxt_hi;
+    const int nrows = row_hi - row_lo;
+    if (tid == 0) n_long = 0;
+    if (tile + (int)gridDim.x < ntiles) { nxt_lo = tile_row[tile + gridDim.x]; nxt_hi = tile_row[tile + gridDim.x + 1]; }
+
+    // ---- phase 1: products from the staged tile ---------------------------------------------------------
+    mbar_wait(&full_bar[stage], parity);
+    if (nrows > 0) {
+      const int* sc = scol + stage * TILE;
+      const double* sv = sval + stage * TILE;
+      int c[PER];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) c[q] = sc[q * SPMV_THREADS + tid];
+      double xv[PER];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const double* src = x + c[q];
+        if (DIST) src = (unsigned)(c[q] - col0) < (unsigned)ncl ? x + (c[q] - col0) : xr + c[q];
+        xv[q] = (hints & 4) ? ld_keep_double_na(src, pol_keep) : ld_keep_double(src, pol_keep);
+      }
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int k = q * SPMV_THREADS + tid;
+        prod[skew(k, sk)] = __dmul_rn(sv[k], xv[q]);
+      }
+    }
+    __syncthreads();                 // products complete; every thread is done reading this stage
+
+    // refill this stage with the tile SPMV_STAGES iterations ahead
+    if (tid == 0) {
+      const int t2 = tile + SPMV_STAGES * gridDim.x;
+      if (t2 < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order the generic-proxy reads before the async writes
+        mbar_expect_tx(&full_bar[stage], TILE * 12);
+        bulk_g2s(scol + stage * TILE, col + (size_t)t2 * TILE, TILE * 4, &full_bar[stage], pol_stream);
+        bulk_g2s(sval + stage * TILE, val + (size_t)t2 * TILE, TILE * 8, &full_bar[stage], pol_stream);
+      }
+    }
+
+    // ---- phase 2: one thread per owned row, sequential ascending sum ------------------------------------
+    for (int j = tid; j < nrows; j += SPMV_THREADS) {
+      const int r = row_lo + j;
+      const int s = row_ptr[r], e = row_ptr[r + 1];
+      if (e - s > SLA_LONG_ROW) {
+        const int slot = atomicAdd(&n_long, 1);
+        long_rows[slot] = r;
+        continue;
+      }
+      const int ks = s - base, ke = e - base;
+      const int kin = ke < TILE ? ke : TILE;
+      double acc = ACC ? yin[r] : 0.0;
+      for (int k = ks; k < kin; ++k) acc = __dadd_rn(acc, prod[skew(k, sk)]);
+      for (int k = (ks > TILE ? ks : TILE); k < ke; ++k) {
+        const int g = base + k;
+        const int cg = col[g];
+        const double xg = DIST ? ((unsigned)(cg - col0) < (unsigned)ncl ? x[cg - col0] : xr[cg]) : x[cg];
+        acc = __dadd_rn(acc, __dmul_rn(val[g], xg));
+      }
+      row_epilogue<EPI>(r, acc, y, u0, e0, e1);
+    }
+    __syncthreads();
+    const int nl = n_long;
+    if (nl > 0) {
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int q = warp; q < nl; q += SPMV_THREADS / 32) {
+        const int r = long_rows[q];
+        const int ks = row_ptr[r] - base, ke = row_ptr[r + 1] - base;
+        double acc = 0.0;
+        for (int k = ks + lane; k < ke; k += 32) {
+          double t;
+          if (k < TILE) t = prod[skew(k, sk)];
+          else {
+            const int g = base + k;
+            const int cg = col[g];
+            const double xg = DIST ? ((unsigned)(cg - col0) < (unsigned)ncl ? x[cg - col0] : xr[cg]) : x[cg];
+            t = __dmul_rn(val[g], xg);
+          }
+          acc += t;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          if (ACC) acc = __dadd_rn(yin[r], acc);
+          row_epilogue<EPI>(r, acc, y, u0, e0, e1);
+        }
+      }
+      __syncthreads();               // long-row readers are done with prod before the next tile overwrites it
+    }
+  }
+
+  if (EPI != EPI_NONE) {
+    double sums[2] = {e0, e1};
+    block_sum<2>(sums, red);
+    if (tid == 0) {
+      partials[blockIdx.x] = sums[0];
+      partials[(size_t)gridDim.x + blockIdx.x] = sums[1];
+    }
+  }
+}
+
 // tile_row[t] = first row r in [0, m] with row_ptr[r] >= t * TILE ; tile_row[ntiles] = m
 __global__ void spmv_plan_kernel(const int* __restrict__ row_ptr, int m, int ntiles, int tile, int* __restrict__ tile_row) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,12 +640,27 @@ static sla_status launch_one(sla_ctx* c, const SpmvArgs& a) {
     if (const char* e = getenv("SLA_SPMV_CARVEOUT"))
       cudaFuncSetAttribute(spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
   }
-  spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST><<<a.ntiles, SPMV_THREADS, 0, c->stream>>>(
-      a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, c->counter, c->scal,
-      EPI != EPI_NONE ? fin_for(c, a.fin) : a.fin, a.dst, (a.hints & 0xff) | (a.skew_a << 8), a.xr, a.col0, a.ncl);
+  int nblk = a.ntiles;
+  if (c->spmv_tma) {
+    // TMA-staged persistent variant: SPMV_CTAS_PER_SM CTAs per SM, each looping over tiles
+    constexpr size_t smem = (size_t)SPMV_STAGES * SLA_SPMV_TILE * 12 + (size_t)(SLA_SPMV_TILE + SLA_SPMV_TILE / 8) * 8;
+    static int attr_set = 0;
+    if (!attr_set) {
+      attr_set = 1;
+      SLA_CUDA(c, cudaFuncSetAttribute(spmv_tma_kernel<SLA_SPMV_TILE, EPI, ACC, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    nblk = a.ntiles < SLA_NUM_SMS * c->spmv_tma ? a.ntiles : SLA_NUM_SMS * c->spmv_tma;
+    spmv_tma_kernel<SLA_SPMV_TILE, EPI, ACC, DIST><<<nblk, SPMV_THREADS, smem, c->stream>>>(
+        a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, a.ntiles,
+        (a.hints & 0xff) | (a.skew_a << 8), a.xr, a.col0, a.ncl);
+  } else {
+    spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST><<<a.ntiles, SPMV_THREADS, 0, c->stream>>>(
+        a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, c->counter, c->scal,
+        EPI != EPI_NONE ? fin_for(c, a.fin) : a.fin, a.dst, (a.hints & 0xff) | (a.skew_a << 8), a.xr, a.col0, a.ncl);
+  }
   SLA_LAUNCH_CHECK(c);
   if (EPI != EPI_NONE) {
-    partials_reduce_kernel<<<1, 1024, 0, c->stream>>>(c->partials, a.ntiles, c->scal, fin_for(c, a.fin), a.dst);
+    partials_reduce_kernel<<<1, 1024, 0, c->stream>>>(c->partials, nblk, c->scal, fin_for(c, a.fin), a.dst);
     SLA_LAUNCH_CHECK(c);
     SLA_TRY(sla_dist_finish_reduction(c, 2, a.fin, a.dst));
   }
