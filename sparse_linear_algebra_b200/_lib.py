@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsla_b200.so")
+LIB_PATH = os.environ.get("SLA_LIB_PATH") or os.path.join(_HERE, "libsla_b200.so")   # SLA_LIB_PATH: tuning experiments only
 
 (SLA_OK, SLA_ERR_SIZE_MISMATCH, SLA_ERR_OOB_INDEX, SLA_ERR_UNSUPPORTED_METHOD, SLA_ERR_NOT_CONVERGED,
  SLA_ERR_BREAKDOWN, SLA_ERR_CUDA, SLA_ERR_COMM, SLA_ERR_ALLOC, SLA_ERR_INVALID) = range(10)

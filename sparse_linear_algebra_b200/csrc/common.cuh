@@ -282,4 +282,6 @@ enum {
   EPI_RESNORM    // sum0 = sum (y - u0)^2 ; y is NOT stored (true-residual check, Sparse.hs:1041)
 };
 
-#define SLA_SPMV_TILE 2048
+#ifndef SLA_SPMV_TILE
+#define SLA_SPMV_TILE 1024     // measured best with 128 threads (8 entries per thread, 16 CTAs/SM): profiles/r01_tile_sweep.txt
+#endif

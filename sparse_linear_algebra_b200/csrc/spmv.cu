@@ -33,7 +33,9 @@
 
 #define SLA_LONG_ROW 256
 #define SLA_LONG_CAP 16
-#define SPMV_THREADS 256
+#ifndef SPMV_THREADS
+#define SPMV_THREADS 128
+#endif
 #define SLA_PANEL_BYTES (40u << 20)     // x bytes per column panel
 #define SLA_PANEL_MIN_X (56u << 20)     // panelise only when 8 n exceeds this ...
 #define SLA_PANEL_MIN_SPAN (24u << 20)  // ... and an average tile touches a wider stretch of x than this
