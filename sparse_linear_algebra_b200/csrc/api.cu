@@ -71,6 +71,10 @@ extern "C" void sla_finalize(sla_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->nccl) sla_dist_detach(c);
   sla_vec_free(c->scratch_x); sla_vec_free(c->scratch_y); sla_vec_free(c->scratch_r);
+  if (c->copy_stream) {
+    cudaStreamDestroy(c->copy_stream);
+    for (int k = 0; k < SLA_MAX_PANELS + 8; ++k) cudaEventDestroy(c->ev_copy[k]);
+  }
   cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->counter); cudaFreeHost(c->h_scal);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
@@ -307,6 +311,8 @@ extern "C" sla_status sla_spmv_host(sla_ctx* c, const sla_csr* A, const double* 
   if (!c || !A || !x_host || !y_host) return SLA_ERR_INVALID;
   SLA_TRY(scratch_vec(c, &c->scratch_x, csr_xdim(A)));
   SLA_TRY(scratch_vec(c, &c->scratch_y, A->m));
+  if (!A->dist && !c->spmv_tma && A->m > 0 && !getenv("SLA_HOST_NO_PIPELINE"))
+    return sla_spmv_host_pipelined(c, A, x_host, y_host, c->scratch_x->d, c->scratch_y->d);
   SLA_CUDA(c, cudaMemcpyAsync(c->scratch_x->d, x_host, sizeof(double) * (size_t)csr_xdim(A), cudaMemcpyHostToDevice, c->stream));
   SLA_TRY(sla_spmv(c, A, c->scratch_x, c->scratch_y));
   SLA_CUDA(c, cudaMemcpyAsync(y_host, c->scratch_y->d, sizeof(double) * (size_t)A->m, cudaMemcpyDeviceToHost, c->stream));

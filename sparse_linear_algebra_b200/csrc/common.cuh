@@ -39,6 +39,8 @@ struct sla_ctx {
   struct sla_vec *scratch_x, *scratch_y;   // device staging for the host-pointer entry points
   struct sla_vec* scratch_r;               // partial row sums of the panelised residual-norm SpMV
   int spmv_hints;            // bit0: matrix stream L2 evict_first, bit1: x gathers L2 evict_last (env SLA_SPMV_HINTS)
+  cudaStream_t copy_stream;  // PCIe copies of the pipelined host-buffer (#>) (spmv.cu)
+  cudaEvent_t ev_copy[SLA_MAX_PANELS + 16];
   int spmv_tma;              // 0: LDG tile kernel; k > 0: TMA-staged persistent kernel with k CTAs per SM (env SLA_SPMV_TMA)
   const void* scal_owner;    // Krylov state whose recurrence scalars currently live in scal[]
   char err[512];
@@ -89,6 +91,7 @@ struct sla_csr {
   sla_panel* panels;         // host array of device pointers
   sla_dist_info* dist;       // non-null: this is the local row block of a distributed matrix (n = GLOBAL columns)
   void* val_bf16;            // bf16 copy of val for the bf16 (##) path, built on first use (spmm.cu)
+  int chunk_ready, chunk_tile[8], chunk_row[8];   // row chunks of the last pass for the pipelined host (#>)
 };
 
 // dimension a vector must have to be multiplied by A / to receive A's product, on this rank
@@ -261,6 +264,7 @@ __device__ __forceinline__ void grid_reduce_finish(double (&mine)[NV], double* p
 sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi,
                            const double* u0, const double* u1, int fin, int dst);
 sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A);
+sla_status sla_spmv_host_pipelined(sla_ctx* c, const sla_csr* A, const double* x_host, double* y_host, double* dx, double* dy);
 void sla_csr_free_panels(sla_csr* A);
 sla_status sla_csr_alloc(sla_ctx* c, int64_t m, int64_t n, int64_t nnz, sla_csr** out);
 sla_status sla_vec_alloc(sla_ctx* c, int64_t n, sla_vec** out);

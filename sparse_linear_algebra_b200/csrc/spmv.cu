@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val,
                  const double* __restrict__ x, const double* yin, double* y, const int* __restrict__ tile_row,
                  const double* __restrict__ u0, double* partials, unsigned int* counter, double* scal,
-                 int fin, int dst, int hints, const double* __restrict__ xr, int col0, int ncl) {
+                 int fin, int dst, int hints, const double* __restrict__ xr, int col0, int ncl, int tile0) {
   constexpr int PER = TILE / SPMV_THREADS;                // entries per thread, lane-contiguous
   __shared__ double prod[TILE + TILE / 8];              // keep CTA smem small: the L1 left over holds the in-flight gathers
   __shared__ double red[2 * 32];
@@ -109,7 +109,7 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
   __shared__ int n_long;
 
   const int tid = threadIdx.x;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x + tile0;                    // tile0 > 0: a row chunk of the host-pipelined (#>)
   const int base = tile * TILE;
   const int row_lo = tile_row[tile], row_hi = tile_row[tile + 1];
   const int nrows = row_hi - row_lo;
@@ -485,12 +485,13 @@ static sla_status build_tile_plan(sla_ctx* c, const int32_t* row_ptr, int64_t m,
 }
 
 void sla_csr_free_panels(sla_csr* A) {
+  A->chunk_ready = 0;
   if (!A->panels) return;
   for (int p = 0; p < A->npanels; ++p) {
     cudaFree(A->panels[p].row_ptr); cudaFree(A->panels[p].col); cudaFree(A->panels[p].val); cudaFree(A->panels[p].tile_row);
   }
   delete[] A->panels;
-  A->panels = nullptr; A->npanels = 0;
+  A->panels = nullptr; A->npanels = 0; A->chunk_ready = 0;
 }
 
 static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
@@ -632,6 +633,7 @@ struct SpmvArgs {
   const double *x, *yin; double* y; const double* u0;
   int fin, dst;
   const double* xr; int col0, ncl;     // DIST only
+  int tile0;                           // first tile of this launch (row-chunked launches of sla_spmv_host)
 };
 
 template <int EPI, bool ACC, bool DIST>
@@ -658,7 +660,7 @@ static sla_status launch_one(sla_ctx* c, const SpmvArgs& a) {
   } else {
     spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST><<<a.ntiles, SPMV_THREADS, 0, c->stream>>>(
         a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, c->counter, c->scal,
-        EPI != EPI_NONE ? fin_for(c, a.fin) : a.fin, a.dst, (a.hints & 0xff) | (a.skew_a << 8), a.xr, a.col0, a.ncl);
+        EPI != EPI_NONE ? fin_for(c, a.fin) : a.fin, a.dst, (a.hints & 0xff) | (a.skew_a << 8), a.xr, a.col0, a.ncl, a.tile0);
   }
   SLA_LAUNCH_CHECK(c);
   if (EPI != EPI_NONE) {
@@ -709,6 +711,7 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   a.ntiles = A->ntiles; a.skew_a = A->skew_a; a.hints = A->hints;
   a.x = x; a.yin = nullptr; a.y = y; a.u0 = u0; a.fin = fin; a.dst = dst;
   a.xr = dist ? A->dist->xfull : nullptr; a.col0 = dist ? (int)A->dist->row0 : 0; a.ncl = dist ? (int)A->m : 0;
+  a.tile0 = 0;
   if (A->npanels < 2) return launch_any(c, epi, false, dist, a);
   // column panels in ascending order; the epilogue rides on the last pass
   double* ybuf = y;
@@ -737,5 +740,72 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
     }
     SLA_TRY(launch_any(c, last ? epi : EPI_NONE, p > 0, dist, a));
   }
+  return SLA_OK;
+}
+
+// ---- (#>) on host buffers, pipelined ------------------------------------------------------------------------
+// sla_spmv_host: x arrives over PCIe panel by panel on a copy stream while the kernels of the earlier column
+// panels run; the last pass is launched in SLA_HOST_CHUNKS row chunks and every finished chunk of y starts its
+// way back to the host while the next chunk computes.  Same kernels, same bits as sla_spmv.
+#define SLA_HOST_CHUNKS 4
+
+static sla_status host_pipe_setup(sla_ctx* c) {
+  if (c->copy_stream) return SLA_OK;
+  SLA_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < SLA_MAX_PANELS + 2 * SLA_HOST_CHUNKS; ++k) SLA_CUDA(c, cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
+  return SLA_OK;
+}
+
+sla_status sla_spmv_host_pipelined(sla_ctx* c, const sla_csr* A, const double* x_host, double* y_host, double* dx, double* dy) {
+  SLA_TRY(host_pipe_setup(c));
+  const int P = A->npanels >= 2 ? A->npanels : 1;
+  const int64_t W = P > 1 ? A->panel_width : A->n;
+  // which tiles / rows form the chunks of the last pass (cached on the matrix)
+  const int32_t* last_tile_row = P > 1 ? A->panels[P - 1].tile_row : A->tile_row;
+  const int last_ntiles = P > 1 ? A->panels[P - 1].ntiles : A->ntiles;
+  sla_csr* Am = const_cast<sla_csr*>(A);
+  if (!Am->chunk_ready) {
+    for (int q = 0; q <= SLA_HOST_CHUNKS; ++q) {
+      const int t = (int)((int64_t)last_ntiles * q / SLA_HOST_CHUNKS);
+      Am->chunk_tile[q] = t;
+      SLA_CUDA(c, cudaMemcpyAsync(&Am->chunk_row[q], last_tile_row + t, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+    Am->chunk_ready = 1;
+  }
+  // 1. uploads, one per column panel, on the copy stream (after everything previously queued on the compute stream)
+  SLA_CUDA(c, cudaEventRecord(c->ev_copy[SLA_MAX_PANELS], c->stream));
+  SLA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy[SLA_MAX_PANELS], 0));
+  for (int p = 0; p < P; ++p) {
+    const int64_t lo = (int64_t)p * W, hi = lo + W < A->n ? lo + W : A->n;
+    if (hi > lo) SLA_CUDA(c, cudaMemcpyAsync(dx + lo, x_host + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyHostToDevice, c->copy_stream));
+    SLA_CUDA(c, cudaEventRecord(c->ev_copy[p], c->copy_stream));
+  }
+  // 2. passes
+  SpmvArgs a;
+  a.hints = A->hints; a.x = dx; a.u0 = nullptr; a.fin = FIN_STORE; a.dst = S_TMP0; a.xr = nullptr; a.col0 = 0; a.ncl = 0;
+  for (int p = 0; p < P; ++p) {
+    const bool last = p + 1 == P;
+    if (P > 1) {
+      const sla_panel& pn = A->panels[p];
+      a.row_ptr = pn.row_ptr; a.col = pn.col; a.val = pn.val; a.tile_row = pn.tile_row; a.ntiles = pn.ntiles; a.skew_a = pn.skew_a;
+    } else {
+      a.row_ptr = A->row_ptr; a.col = A->col; a.val = A->val; a.tile_row = A->tile_row; a.ntiles = A->ntiles; a.skew_a = A->skew_a;
+    }
+    a.yin = p == 0 ? nullptr : dy; a.y = dy; a.tile0 = 0;
+    SLA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[p], 0));
+    if (!last) { SLA_TRY(launch_any(c, EPI_NONE, p > 0, false, a)); continue; }
+    for (int q = 0; q < SLA_HOST_CHUNKS; ++q) {
+      const int t0 = A->chunk_tile[q], t1 = A->chunk_tile[q + 1];
+      const int r0 = A->chunk_row[q], r1 = q + 1 == SLA_HOST_CHUNKS ? (int)A->m : A->chunk_row[q + 1];
+      if (t1 > t0) { a.tile0 = t0; a.ntiles = t1 - t0; SLA_TRY(launch_any(c, EPI_NONE, p > 0, false, a)); }
+      cudaEvent_t ev = c->ev_copy[SLA_MAX_PANELS + 1 + q];
+      SLA_CUDA(c, cudaEventRecord(ev, c->stream));
+      SLA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, ev, 0));
+      if (r1 > r0) SLA_CUDA(c, cudaMemcpyAsync(y_host + r0, dy + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+  }
+  SLA_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  SLA_CUDA(c, cudaStreamSynchronize(c->stream));
   return SLA_OK;
 }

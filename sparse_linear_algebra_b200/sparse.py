@@ -370,6 +370,14 @@ class SpMatrix:
         return SpMatrix(ctx, h)
 
     @staticmethod
+    def fromMatrixMarket(path, ctx=None):
+        """Coordinate real Matrix Market file -> device matrix (fromListSM semantics for duplicates)."""
+        from .mmio import read_matrix_market
+
+        m, n, i, j, v = read_matrix_market(path)
+        return SpMatrix.fromCOO((m, n), i, j, v, ctx)
+
+    @staticmethod
     def eye(n, ctx=None):
         return SpMatrix.mkDiagonal(n, np.ones(n), ctx)
 

@@ -278,6 +278,7 @@ def test_spmv_column_panels_bit_exact(sla, o, monkeypatch, panels):
     lens = np.diff(rp)
     short = lens <= 256                      # every per-panel segment of such a row is summed sequentially
     assert y[short].tobytes() == yo[short].tobytes()
+    assert A.matVecHost(x).tobytes() == y.tobytes()      # host-buffer entry: panel-wise upload, chunked download
     absum = np.array([np.abs(va[rp[r]:rp[r + 1]] * x[ci[rp[r]:rp[r + 1]]]).sum() for r in range(m)])
     assert np.all(np.abs(y - yo) <= (lens + 2) * U * absum)
     # Krylov epilogues (fused dots, residual norm) through the panel path: cfg-1 system, same iteration count
