@@ -27,6 +27,8 @@
 #define SLA_GEN_BANDED    1 /* diag + (k-1) distinct hashed columns within +-band of the row      */
 #define SLA_GEN_LAPLACE2D 2 /* 5-point Laplacian on a band x band grid (n = band*band), Dirichlet */
 
+#define SLA_GEN_BLOCK16   3 /* block-structured: every 16-row group holds k/16 full 16 x 16 blocks at hashed block columns */
+
 #define SLA_SYNTH_MAX_K 128 /* max stored entries per generated row */
 
 #define SLA_SALT_VAL 0xA5A5F00DBAADC0DEULL
@@ -60,6 +62,13 @@ SLA_HD int sla_synth_row_len(int kind, int64_t n, int k, int64_t band, int64_t i
     int64_t g = band, ix = i % g, iy = i / g;
     return 1 + (iy > 0) + (ix > 0) + (ix < g - 1) + (iy < g - 1);
   }
+  if (kind == SLA_GEN_BLOCK16) {
+    int nb = k / 16;
+    if (nb < 1) nb = 1;
+    if (nb > SLA_SYNTH_MAX_K / 16) nb = SLA_SYNTH_MAX_K / 16;
+    const int64_t nbc = n / 16;
+    return (int)(16 * (nb < nbc ? nb : nbc));
+  }
   int64_t lo = 0, hi = n - 1;
   if (kind == SLA_GEN_BANDED) {
     lo = i - band < 0 ? 0 : i - band;
@@ -84,6 +93,32 @@ SLA_HD int sla_synth_row(int kind, int64_t n, int k, uint64_t seed, int64_t band
     if (ix < g - 1) { cols[c] = i + 1; vals[c] = -1.0; ++c; }
     if (iy < g - 1) { cols[c] = i + g; vals[c] = -1.0; ++c; }
     return c;
+  }
+  if (kind == SLA_GEN_BLOCK16) {
+    /* the block columns depend only on the 16-row group, so the 16 rows of a group share their blocks */
+    const int nb = sla_synth_row_len(kind, n, k, band, i) / 16;
+    const int64_t grp = i / 16, nbc = n / 16;
+    int64_t bc[SLA_SYNTH_MAX_K / 16];
+    int cnt = 0;
+    for (uint64_t a = 0; cnt < nb; ++a) {
+      const int64_t c = (int64_t)(sla_hash3(seed, (uint64_t)grp, a) % (uint64_t)nbc);
+      int dup = 0;
+      for (int q = 0; q < cnt; ++q) dup |= (bc[q] == c);
+      if (!dup) bc[cnt++] = c;
+    }
+    for (int a = 1; a < cnt; ++a) {
+      const int64_t c = bc[a];
+      int b = a - 1;
+      while (b >= 0 && bc[b] > c) { bc[b + 1] = bc[b]; --b; }
+      bc[b + 1] = c;
+    }
+    int o = 0;
+    for (int a = 0; a < cnt; ++a)
+      for (int q = 0; q < 16; ++q, ++o) {
+        cols[o] = bc[a] * 16 + q;
+        vals[o] = sla_u11(sla_hash3(seed ^ SLA_SALT_VAL, (uint64_t)i, (uint64_t)o));
+      }
+    return o;
   }
   int64_t lo = 0, hi = n - 1;
   if (kind == SLA_GEN_BANDED) {

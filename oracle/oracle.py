@@ -16,7 +16,7 @@ _SO = os.path.join(_HERE, "libsla_oracle.so")
 
 ORA_OK, ORA_ERR_SIZE_MISMATCH, ORA_ERR_OOB_INDEX, ORA_ERR_UNSUPPORTED_METHOD = 0, 1, 2, 3
 GMRES_, CGNE_, BCG_, CGS_, BICGSTAB_ = 0, 1, 2, 3, 4
-GEN_UNIFORM, GEN_BANDED, GEN_LAPLACE2D = 0, 1, 2
+GEN_UNIFORM, GEN_BANDED, GEN_LAPLACE2D, GEN_BLOCK16 = 0, 1, 2, 3
 
 
 class OracleError(Exception):

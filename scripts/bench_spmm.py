@@ -7,7 +7,7 @@ kind, n = sys.argv[1], int(sys.argv[2])
 band = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 k = 128
 ctx = sla.default_context()
-gk = {"uniform": sla.GEN_UNIFORM, "banded": sla.GEN_BANDED}[kind]
+gk = {"uniform": sla.GEN_UNIFORM, "banded": sla.GEN_BANDED, "block16": sla.GEN_BLOCK16}[kind]
 A = sla.SpMatrix.generate(gk, n, 32, 5, band)
 rng = np.random.default_rng(0)
 Bh = rng.uniform(-1, 1, (min(n, 1 << 16), k))

@@ -10,7 +10,7 @@ from ._lib import LIB_PATH, SolveOpts
 _lib.load()   # fail loudly when the CUDA extension is missing
 
 from .sparse import (  # noqa: E402
-    BCG_, BF16, BICGSTAB_, CGNE_, CGS_, F64, GMRES_, GEN_BANDED, GEN_LAPLACE2D, GEN_UNIFORM, Context, DenseBlock, DenseMatrix, IterE,
+    BCG_, BF16, BICGSTAB_, CGNE_, CGS_, F64, GMRES_, GEN_BANDED, GEN_BLOCK16, GEN_LAPLACE2D, GEN_UNIFORM, Context, DenseBlock, DenseMatrix, IterE,
     KrylovState, MatVecSizeMismatchException, OutOfBoundsIndexError, SlaError, SpMatrix, SpVector, arnoldi,
     backslash, bicgsInit, bicgstabStep, cgneInit, cgneStep, cgsInit, cgsStep, default_context, gmres, linSolve0,
     linSolve0Host, set_default_context,

@@ -91,6 +91,7 @@ struct sla_csr {
   sla_panel* panels;         // host array of device pointers
   sla_dist_info* dist;       // non-null: this is the local row block of a distributed matrix (n = GLOBAL columns)
   void* val_bf16;            // bf16 copy of val for the bf16 (##) path, built on first use (spmm.cu)
+  int bsr_ready, bsr_nbr, bsr_nblk; int *bsr_row_ptr, *bsr_col; void* bsr_val;   // 16 x 16 bf16 block copy for the tcgen05 (##) path
   int chunk_ready, chunk_tile[8], chunk_row[8];   // row chunks of the last pass for the pipelined host (#>)
 };
 
@@ -276,6 +277,7 @@ sla_status sla_dist_exchange_panel(sla_ctx* c, const sla_csr* A, const double* x
 sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P);                                   // spmv.cu
 sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count);
 void sla_csr_free_dist(sla_csr* A);
+void sla_csr_free_bsr(sla_csr* A);
 static inline int fin_for(const sla_ctx* c, int fin) { return c->world > 1 ? (fin | FIN_DEFER) : fin; }
 
 // SpMV epilogues

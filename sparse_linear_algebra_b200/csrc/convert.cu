@@ -48,6 +48,7 @@ extern "C" void sla_csr_free(sla_csr* A) {
   if (A->T) sla_csr_free(A->T);
   sla_csr_free_panels(A);
   sla_csr_free_dist(A);
+  sla_csr_free_bsr(A);
   cudaFree(A->row_ptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->tile_row); cudaFree(A->val_bf16);
   delete A;
 }
@@ -386,7 +387,8 @@ extern "C" sla_status sla_csr_col_range(sla_ctx* c, const sla_csr* A, int64_t* l
 extern "C" sla_status sla_csr_generate_rows(sla_ctx* c, int kind, int64_t n, int nnz_per_row, uint64_t seed, int64_t band,
                                             int64_t row_lo, int64_t row_hi, sla_csr** out) {
   if (!c || !out || n <= 0 || nnz_per_row < 1 || row_lo < 0 || row_hi < row_lo || row_hi > n) return SLA_ERR_INVALID;
-  if (kind != SLA_GEN_UNIFORM && kind != SLA_GEN_BANDED && kind != SLA_GEN_LAPLACE2D) return sla_fail(c, SLA_ERR_INVALID, "generate: unknown kind");
+  if (kind != SLA_GEN_UNIFORM && kind != SLA_GEN_BANDED && kind != SLA_GEN_LAPLACE2D && kind != SLA_GEN_BLOCK16) return sla_fail(c, SLA_ERR_INVALID, "generate: unknown kind");
+  if (kind == SLA_GEN_BLOCK16 && n % 16 != 0) return sla_fail(c, SLA_ERR_INVALID, "generate: block16 needs n to be a multiple of 16");
   if (kind == SLA_GEN_LAPLACE2D && band * band != n) return sla_fail(c, SLA_ERR_INVALID, "generate: laplace2d needs n = band*band");
   if (kind == SLA_GEN_BANDED && band < 1) return sla_fail(c, SLA_ERR_INVALID, "generate: banded needs band >= 1");
   *out = nullptr;

@@ -16,7 +16,11 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
+#include <cub/device/device_scan.cuh>
 #include <new>
+#include <stdlib.h>
+
+sla_status sla_spmm_bsr_tc(sla_ctx* c, const sla_csr* A, const sla_dense* B, sla_dense* C, double min_fill);
 
 #define SPMM_THREADS 256
 
@@ -178,10 +182,228 @@ extern "C" sla_status sla_spmm_dense(sla_ctx* c, const sla_csr* A, const sla_den
   if (B->dtype == SLA_F64) {
     spmm_f64_kernel<<<(unsigned)blocks, SPMM_THREADS, 0, c->stream>>>(A->row_ptr, A->col, A->val, (const double*)B->d, (double*)C->d, m, k);
   } else {
+    // block-structured A and a 128-column B: tensor-core tile path (SLA_SPMM_TC=0 disables, =1 forces)
+    const char* tc = getenv("SLA_SPMM_TC");
+    if (!(tc && atoi(tc) == 0)) {
+      const sla_status ts = sla_spmm_bsr_tc(c, A, B, C, tc && atoi(tc) == 1 ? 0.0 : 0.5);
+      if (ts == SLA_OK) return SLA_OK;
+      if (ts != SLA_ERR_INVALID) return ts;
+    }
     SLA_TRY(ensure_val_bf16(c, A));
     spmm_bf16_kernel<<<(unsigned)blocks, SPMM_THREADS, 0, c->stream>>>(A->row_ptr, A->col, (const __nv_bfloat16*)A->val_bf16,
                                                                       (const __nv_bfloat16*)B->d, (__nv_bfloat16*)C->d, m, k);
   }
+  SLA_LAUNCH_CHECK(c);
+  return SLA_OK;
+}
+
+// =================================================================================================================
+// Tensor-core tile path (tcgen05 + TMEM) for block-structured A and a 128-column bf16 B.
+//
+// A is re-blocked once into 16 x 16 bf16 blocks (BSR).  For one block row the product is computed TRANSPOSED,
+//     C^T[128 x 16] += Bslab^T[128 x 16] * Ablk^T[16 x 16]        (M = 128 columns of B, N = 16 rows, K = 16)
+// so that one tcgen05.mma (kind::f16, M128 N16 K16, fp32 accumulator in TMEM) consumes a whole block: the 16 rows
+// of B the block touches are staged ONCE in shared memory and reused by all 16 rows of the block — that reuse, not
+// the flops, is what the gather kernel lacks (it re-reads a B row per stored entry and is L2-bound).
+//   operand A of the MMA = Bslab^T, MN-major, no-swizzle canonical layout (8 x 16-byte core matrices,
+//                          SBO = 128 B between cores along M, LBO = 2048 B between the two K halves)
+//   operand B of the MMA = Ablk^T,  K-major,  no-swizzle canonical layout (SBO = 256 B, LBO = 128 B); the BSR
+//                          values are stored in that order at conversion time, so staging a block is a 512 B copy.
+// One CTA of 128 threads walks block rows; thread t owns TMEM lane t = column t of C for the epilogue
+// (tcgen05.ld 32x32b.x16), fp32 -> bf16, stores 64 B per warp per row.
+#define BSR_B 16
+
+__global__ void bsr_count_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int m, int nbr, int* __restrict__ cnt) {
+  const int br = blockIdx.x * blockDim.x + threadIdx.x;
+  if (br >= nbr) return;
+  int cur[BSR_B], end[BSR_B];
+  for (int i = 0; i < BSR_B; ++i) {
+    const int r = br * BSR_B + i;
+    cur[i] = r < m ? row_ptr[r] : 0;
+    end[i] = r < m ? row_ptr[r + 1] : 0;
+  }
+  int n = 0;
+  for (;;) {
+    int mn = 0x7fffffff;
+    for (int i = 0; i < BSR_B; ++i) if (cur[i] < end[i]) mn = min(mn, col[cur[i]] >> 4);
+    if (mn == 0x7fffffff) break;
+    ++n;
+    for (int i = 0; i < BSR_B; ++i) while (cur[i] < end[i] && (col[cur[i]] >> 4) == mn) ++cur[i];
+  }
+  cnt[br] = n;
+}
+
+__global__ void bsr_fill_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val, int m,
+                                int nbr, const int* __restrict__ brow_ptr, int* __restrict__ bcol, __nv_bfloat16* __restrict__ bval) {
+  const int br = blockIdx.x * blockDim.x + threadIdx.x;
+  if (br >= nbr) return;
+  int cur[BSR_B], end[BSR_B];
+  for (int i = 0; i < BSR_B; ++i) {
+    const int r = br * BSR_B + i;
+    cur[i] = r < m ? row_ptr[r] : 0;
+    end[i] = r < m ? row_ptr[r + 1] : 0;
+  }
+  int b = brow_ptr[br];
+  for (;;) {
+    int mn = 0x7fffffff;
+    for (int i = 0; i < BSR_B; ++i) if (cur[i] < end[i]) mn = min(mn, col[cur[i]] >> 4);
+    if (mn == 0x7fffffff) break;
+    bcol[b] = mn;
+    __nv_bfloat16* blk = bval + (size_t)b * 256;
+    for (int i = 0; i < BSR_B; ++i)
+      while (cur[i] < end[i] && (col[cur[i]] >> 4) == mn) {
+        const int k = col[cur[i]] & 15;
+        // canonical K-major core-matrix order of the MMA's B operand: element (n = i, k)
+        blk[(i >> 3) * 128 + (k >> 3) * 64 + (i & 7) * 8 + (k & 7)] = __double2bfloat16(val[cur[i]]);
+        ++cur[i];
+      }
+    ++b;
+  }
+}
+
+__device__ __forceinline__ uint32_t spmm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // SmemDescriptor: start [0,14) >>4 | LBO [16,30) >>4 | SBO [32,46) >>4 | version = 1 at [46,48) | layout_type = 0 (no swizzle)
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) |
+         (1ULL << 46);
+}
+
+__global__ void __launch_bounds__(128)
+spmm_bsr_tc_kernel(const int* __restrict__ brow_ptr, const int* __restrict__ bcol, const __nv_bfloat16* __restrict__ bval,
+                   const __nv_bfloat16* __restrict__ B, __nv_bfloat16* __restrict__ C, int m, int nbr) {
+  __shared__ __align__(128) __nv_bfloat16 sA[256];          // one 16 x 16 block of A (operand B of the MMA)
+  __shared__ __align__(128) __nv_bfloat16 sB[16 * 128];     // 16 rows of B (operand A of the MMA), canonical MN-major
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(spmm_smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(spmm_smem_u32(&mma_bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  // kind::f16 instruction descriptor: D = F32, A = B = BF16, A MN-major, B K-major, N = 16, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint64_t adesc = umma_desc(spmm_smem_u32(sB), 2048, 128);
+  const uint64_t bdesc = umma_desc(spmm_smem_u32(sA), 128, 256);
+  uint32_t phase = 0;
+
+  for (int br = blockIdx.x; br < nbr; br += gridDim.x) {
+    const int s = brow_ptr[br], e = brow_ptr[br + 1];
+    for (int b = s; b < e; ++b) {
+      // stage the A block (already in canonical order) and the 16 B rows it multiplies
+      if (tid < 32) reinterpret_cast<uint4*>(sA)[tid] = reinterpret_cast<const uint4*>(bval + (size_t)b * 256)[tid];
+      const size_t brow0 = (size_t)bcol[b] * 16;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int q = tid + 128 * j, k = q >> 4, mc = q & 15;
+        const uint4 v = *reinterpret_cast<const uint4*>(B + (brow0 + k) * 128 + mc * 8);
+        *reinterpret_cast<uint4*>(sB + mc * 64 + (k >> 3) * 1024 + (k & 7) * 8) = v;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = b > s ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(spmm_smem_u32(&mma_bar)) : "memory");
+      }
+      // wait until the MMA has consumed the staged operands (single-buffered) / produced the accumulator
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "SPMM_WAIT:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra SPMM_DONE;\n\t"
+          "bra SPMM_WAIT;\n\t"
+          "SPMM_DONE:\n\t}" ::"r"(spmm_smem_u32(&mma_bar)), "r"(phase) : "memory");
+      phase ^= 1u;
+    }
+    // epilogue: thread t = TMEM lane t = column t of C; 16 accumulator columns = the 16 rows of this block row
+    uint32_t r[16];
+    if (e > s) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int row = br * 16 + i;
+      if (row < m) C[(size_t)row * 128 + tid] = __float2bfloat16_rn(__uint_as_float(r[i]));
+    }
+    // every lane has drained its accumulator before the next block row's first MMA overwrites it
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+}
+
+// Builds the BSR copy of A on first use; returns the fill ratio nnz / (16*16*nblocks) through *fill.
+static sla_status ensure_bsr(sla_ctx* c, const sla_csr* A, double* fill) {
+  sla_csr* Am = const_cast<sla_csr*>(A);
+  if (!Am->bsr_ready) {
+    const int m = (int)A->m, nbr = (m + BSR_B - 1) / BSR_B;
+    int *cnt = nullptr; void* tmp = nullptr;
+    SLA_CUDA(c, cudaMalloc(&cnt, sizeof(int) * (size_t)(nbr + 1)));
+    SLA_CUDA(c, cudaMalloc(&Am->bsr_row_ptr, sizeof(int) * (size_t)(nbr + 1)));
+    SLA_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(nbr + 1), c->stream));
+    bsr_count_kernel<<<(nbr + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, A->col, m, nbr, cnt);
+    SLA_LAUNCH_CHECK(c);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, Am->bsr_row_ptr, nbr + 1, c->stream);
+    SLA_CUDA(c, cudaMalloc(&tmp, tb ? tb : 1));
+    cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, Am->bsr_row_ptr, nbr + 1, c->stream);
+    c->launches += 2;
+    int nblk = 0;
+    SLA_CUDA(c, cudaMemcpyAsync(&nblk, Am->bsr_row_ptr + nbr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(cnt); cudaFree(tmp);
+    Am->bsr_nblk = nblk; Am->bsr_nbr = nbr;
+    SLA_CUDA(c, cudaMalloc(&Am->bsr_col, sizeof(int) * (size_t)(nblk > 0 ? nblk : 1)));
+    SLA_CUDA(c, cudaMalloc(&Am->bsr_val, 512 * (size_t)(nblk > 0 ? nblk : 1)));
+    SLA_CUDA(c, cudaMemsetAsync(Am->bsr_val, 0, 512 * (size_t)(nblk > 0 ? nblk : 1), c->stream));
+    bsr_fill_kernel<<<(nbr + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, A->col, A->val, m, nbr, Am->bsr_row_ptr, Am->bsr_col,
+                                                              (__nv_bfloat16*)Am->bsr_val);
+    SLA_LAUNCH_CHECK(c);
+    Am->bsr_ready = 1;
+  }
+  *fill = A->bsr_nblk > 0 ? (double)A->nnz / (256.0 * (double)A->bsr_nblk) : 0.0;
+  return SLA_OK;
+}
+
+void sla_csr_free_bsr(sla_csr* A) {
+  cudaFree(A->bsr_row_ptr); cudaFree(A->bsr_col); cudaFree(A->bsr_val);
+  A->bsr_row_ptr = nullptr; A->bsr_col = nullptr; A->bsr_val = nullptr; A->bsr_ready = 0;
+}
+
+// C = A ## B on the tensor cores; returns SLA_ERR_INVALID (without touching C) when the path does not apply.
+sla_status sla_spmm_bsr_tc(sla_ctx* c, const sla_csr* A, const sla_dense* B, sla_dense* C, double min_fill) {
+  if (B->dtype != SLA_BF16 || B->cols != 128 || A->n % 16 != 0 || A->m == 0) return SLA_ERR_INVALID;   // whole 16-row slabs of B only
+  double fill = 0;
+  SLA_TRY(ensure_bsr(c, A, &fill));
+  if (fill < min_fill) return SLA_ERR_INVALID;
+  int grid = A->bsr_nbr < SLA_NUM_SMS * 16 ? A->bsr_nbr : SLA_NUM_SMS * 16;
+  if (grid < 1) grid = 1;
+  spmm_bsr_tc_kernel<<<grid, 128, 0, c->stream>>>(A->bsr_row_ptr, A->bsr_col, (const __nv_bfloat16*)A->bsr_val,
+                                                 (const __nv_bfloat16*)B->d, (__nv_bfloat16*)C->d, (int)A->m, A->bsr_nbr);
   SLA_LAUNCH_CHECK(c);
   return SLA_OK;
 }

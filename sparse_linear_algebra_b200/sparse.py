@@ -30,7 +30,7 @@ import numpy as np
 from . import _lib as L
 
 GMRES_, CGNE_, BCG_, CGS_, BICGSTAB_ = 0, 1, 2, 3, 4          # LinSolveMethod, Sparse.hs:1007-1012
-GEN_UNIFORM, GEN_BANDED, GEN_LAPLACE2D = 0, 1, 2              # include/sla_synth.h
+GEN_UNIFORM, GEN_BANDED, GEN_LAPLACE2D, GEN_BLOCK16 = 0, 1, 2, 3              # include/sla_synth.h
 
 
 class SlaError(Exception):

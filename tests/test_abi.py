@@ -66,3 +66,32 @@ def test_solve_opts_defaults(lib):
     L.sla_solve_opts_default(C.byref(o))
     # nits = 200, tolAbs = 1e-6, tolRel = 1e-4   (Sparse.hs:1034-1036)
     assert (o.max_iters, o.tol_abs, o.tol_rel, o.true_residual, o.check_every) == (200, 1e-6, 1e-4, 1, 1)
+
+
+def _build_c_smoke(tmp_path):
+    import subprocess
+
+    exe = os.path.join(str(tmp_path), "abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                           "-L", os.path.join(ROOT, "sparse_linear_algebra_b200"), "-lsla_b200", "-lm",
+                           "-Wl,-rpath," + os.path.join(ROOT, "sparse_linear_algebra_b200"), "-o", exe])
+    return exe
+
+
+def test_c_program_links_against_the_abi(lib, tmp_path):
+    """A plain C99 program compiles against include/sla_b200.h and links to the .so; without a GPU it exits 77."""
+    import subprocess
+
+    exe = _build_c_smoke(tmp_path)
+    rc = subprocess.run([exe], capture_output=True, text=True).returncode
+    assert rc in (0, 77)
+
+
+@pytest.mark.gpu
+def test_c_program_runs_on_gpu(lib, tmp_path):
+    import subprocess
+
+    exe = _build_c_smoke(tmp_path)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "abi_smoke ok" in p.stdout

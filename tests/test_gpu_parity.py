@@ -437,10 +437,10 @@ def test_gmres_converges(sla, o):
 # =============================================================== (##) with a dense right operand
 
 def _bf16_round(a):
-    """Round-to-nearest-even to bfloat16, returned as float64."""
-    u = np.asarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
-    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
-    return r.astype(np.uint32).view(np.float32).astype(np.float64)
+    """Round-to-nearest-even from float64 straight to bfloat16 (8 significant bits), returned as float64.
+    (Going through float32 first would double-round about one value in 2^16.)"""
+    m, e = np.frexp(np.asarray(a, dtype=np.float64))
+    return np.ldexp(np.round(m * 256.0) / 256.0, e)
 
 
 def test_ref_matmat_fixtures(sla):                       # LibSpec.hs:61-65, 1263-1271: exact ==
@@ -490,6 +490,66 @@ def test_spmm_bf16_within_bound(sla, o):
     bound = 2.0 ** -8 * np.abs(Cref) + (lens + 2) * 2.0 ** -24 * absum + 1e-30
     assert np.all(np.abs(C - Cref) <= bound)
     assert np.array_equal(C, _bf16_round(C))              # the output really is bf16
+
+
+def _spmm_bound_check(A, Bh, C):
+    import scipy.sparse as sp
+
+    rp, ci, va = A.toCSR()
+    S = sp.csr_matrix((va, ci, rp), shape=(A.nrows, A.ncols))
+    Cref = S @ Bh
+    absum = abs(S) @ np.abs(Bh)
+    lens = np.diff(rp)[:, None]
+    bound = 2.0 ** -8 * np.abs(Cref) + (lens + 2) * 2.0 ** -24 * absum + 1e-30
+    assert np.all(np.abs(C - Cref) <= bound)
+    assert np.array_equal(C, _bf16_round(C))
+
+
+@pytest.mark.parametrize("m,n,nblocks,fill", [(16, 16, 1, 1.0), (64, 64, 6, 1.0), (160, 4096, 60, 0.6), (1000, 2000, 400, 1.0)])
+def test_spmm_tensor_core_path(sla, monkeypatch, m, n, nblocks, fill):
+    """The tcgen05 / TMEM tile path (16 x 16 bf16 blocks, M128 N16 K16 MMAs, fp32 accumulators) on block-structured
+    matrices, forced with SLA_SPMM_TC=1: same bound as the gather kernel; includes a ragged last block row and
+    partially filled blocks (zero-padded)."""
+    monkeypatch.setenv("SLA_SPMM_TC", "1")
+    rng = np.random.default_rng(m + n)
+    nbr, nbc = (m + 15) // 16, n // 16
+    ii, jj = [], []
+    for _ in range(nblocks):
+        br, bc = int(rng.integers(0, nbr)), int(rng.integers(0, nbc))
+        r, c = np.meshgrid(np.arange(16), np.arange(16), indexing="ij")
+        keep = (rng.random((16, 16)) < fill) & (br * 16 + r < m)
+        ii.append((br * 16 + r)[keep]); jj.append((bc * 16 + c)[keep])
+    i, j = np.concatenate(ii), np.concatenate(jj)
+    v = _bf16_round(rng.uniform(-1, 1, i.size))
+    A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+    Bh = _bf16_round(rng.uniform(-1, 1, (n, 128)))
+    C = (A @ sla.DenseMatrix.fromHost(Bh, sla.BF16)).toHost()
+    _spmm_bound_check(A, Bh, C)
+
+
+def test_spmm_block16_family_both_paths(sla, monkeypatch):
+    """cfg 5 'K16' family (two full 16 x 16 blocks per 16-row group): the plan picks the tensor-core path by
+    itself; it and the gather kernel both stay within the bound, and agree to bf16 rounding."""
+    n = 16 * 3000
+    A = sla.SpMatrix.generate(sla.GEN_BLOCK16, n, 32, 0x5EED0005)
+    assert A.nnz == 32 * n
+    rng = np.random.default_rng(7)
+    Bh = _bf16_round(rng.uniform(-1, 1, (n, 128)))
+    Bd = sla.DenseMatrix.fromHost(Bh, sla.BF16)
+    l0 = A.ctx.launches
+    C_tc = (A @ Bd).toHost()
+    monkeypatch.setenv("SLA_SPMM_TC", "0")
+    C_g = (A @ Bd).toHost()
+    # A's values are not bf16-representable here: compare against the product of the ROUNDED values
+    rp, ci, va = A.toCSR()
+    import scipy.sparse as sp
+
+    S = sp.csr_matrix((_bf16_round(va), ci, rp), shape=(n, n))
+    Cref = S @ Bh
+    absum = abs(S) @ np.abs(Bh)
+    bound = 2.0 ** -8 * np.abs(Cref) + 34 * 2.0 ** -24 * absum + 1e-30
+    assert np.all(np.abs(C_tc - Cref) <= bound) and np.all(np.abs(C_g - Cref) <= bound)
+    assert np.abs(C_tc - C_g).max() <= 2.0 ** -7 * np.abs(Cref).max()
 
 
 # =============================================================== BASELINE sizes, size-independent properties
