@@ -268,11 +268,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          (1ULL << 46);
 }
 
+#ifndef TC_STAGE
+#define TC_STAGE 2
+#endif
+//      // blocks staged (and multiplied) per synchronisation
+
 __global__ void __launch_bounds__(128)
 spmm_bsr_tc_kernel(const int* __restrict__ brow_ptr, const int* __restrict__ bcol, const __nv_bfloat16* __restrict__ bval,
                    const __nv_bfloat16* __restrict__ B, __nv_bfloat16* __restrict__ C, int m, int nbr) {
-  __shared__ __align__(128) __nv_bfloat16 sA[256];          // one 16 x 16 block of A (operand B of the MMA)
-  __shared__ __align__(128) __nv_bfloat16 sB[16 * 128];     // 16 rows of B (operand A of the MMA), canonical MN-major
+  __shared__ __align__(128) __nv_bfloat16 sA[TC_STAGE][256];          // 16 x 16 blocks of A (operand B of the MMA)
+  __shared__ __align__(128) __nv_bfloat16 sB[TC_STAGE][16 * 128];     // 16 rows of B each (operand A), canonical MN-major
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -291,34 +296,54 @@ spmm_bsr_tc_kernel(const int* __restrict__ brow_ptr, const int* __restrict__ bco
   const uint32_t tmem = tmem_base_s;
   // kind::f16 instruction descriptor: D = F32, A = B = BF16, A MN-major, B K-major, N = 16, M = 128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-  const uint64_t adesc = umma_desc(spmm_smem_u32(sB), 2048, 128);
-  const uint64_t bdesc = umma_desc(spmm_smem_u32(sA), 128, 256);
   uint32_t phase = 0;
 
   for (int br = blockIdx.x; br < nbr; br += gridDim.x) {
     const int s = brow_ptr[br], e = brow_ptr[br + 1];
-    for (int b = s; b < e; ++b) {
-      // stage the A block (already in canonical order) and the 16 B rows it multiplies
-      if (tid < 32) reinterpret_cast<uint4*>(sA)[tid] = reinterpret_cast<const uint4*>(bval + (size_t)b * 256)[tid];
-      const size_t brow0 = (size_t)bcol[b] * 16;
+    for (int b0 = s; b0 < e; b0 += TC_STAGE) {
+      const int nb = e - b0 < TC_STAGE ? e - b0 : TC_STAGE;
+      // stage nb blocks of A (already in canonical order) and the 16 B rows each of them multiplies; all the
+      // global loads of the stage are issued before the first store so that they overlap
+      uint4 av[TC_STAGE], bv[TC_STAGE][2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int q = tid + 128 * j, k = q >> 4, mc = q & 15;
-        const uint4 v = *reinterpret_cast<const uint4*>(B + (brow0 + k) * 128 + mc * 8);
-        *reinterpret_cast<uint4*>(sB + mc * 64 + (k >> 3) * 1024 + (k & 7) * 8) = v;
+      for (int j = 0; j < TC_STAGE; ++j) {
+        if (j < nb) {
+          if (tid < 32) av[j] = reinterpret_cast<const uint4*>(bval + (size_t)(b0 + j) * 256)[tid];
+          const size_t brow0 = (size_t)bcol[b0 + j] * 16;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int q = tid + 128 * h, k = q >> 4, mc = q & 15;
+            bv[j][h] = *reinterpret_cast<const uint4*>(B + (brow0 + k) * 128 + mc * 8);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < TC_STAGE; ++j) {
+        if (j < nb) {
+          if (tid < 32) reinterpret_cast<uint4*>(sA[j])[tid] = av[j];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int q = tid + 128 * h, k = q >> 4, mc = q & 15;
+            *reinterpret_cast<uint4*>(sB[j] + mc * 64 + (k >> 3) * 1024 + (k & 7) * 8) = bv[j][h];
+          }
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
       __syncthreads();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = b > s ? 1u : 0u;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+        for (int j = 0; j < nb; ++j) {
+          const uint64_t adesc = umma_desc(spmm_smem_u32(sB[j]), 2048, 128);
+          const uint64_t bdesc = umma_desc(spmm_smem_u32(sA[j]), 128, 256);
+          const uint32_t acc = (b0 + j) > s ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+              ::"r"(tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(spmm_smem_u32(&mma_bar)) : "memory");
       }
-      // wait until the MMA has consumed the staged operands (single-buffered) / produced the accumulator
+      // wait until the MMAs have consumed the staged operands / produced the accumulator
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
           "SPMM_WAIT:\n\t"
