@@ -285,13 +285,29 @@ def run_gpu(args):
         extra["arnoldi_cfg4_ms_per_cycle"] = s4 * 1e3
         extra["arnoldi_cfg4_gbs"] = b4bytes / s4 / 1e9
         del A4, Qd
+        # ---- config 5: (##) CSR 10M x 10M x dense 10M x 128 bf16 (single GPU: ## is not row-partitioned yet).
+        # K16 = block-structured family (tcgen05 tile path); U = uniform columns (gather kernel, L2-bound).
+        if world == 1:
+            k5 = 128
+            B5 = sla.DenseMatrix.generate(n, k5, 0x5EED0055, sla.BF16)
+            C5 = sla.DenseMatrix.zeros(n, k5, sla.BF16)
+            for tag, kind in (("k16", sla.GEN_BLOCK16), ("uniform", sla.GEN_UNIFORM)):
+                A5 = sla.SpMatrix.generate(kind, n, 32, 0x5EED0005)
+                reps = 5 if tag == "k16" else 2
+                ms5, _ = timed(lambda: A5.matMat(B5, out=C5), reps, 1)
+                b5 = 6 * A5.nnz + 4 * (n + 1) + 4 * n * k5        # B_spmm, SURVEY.md §8(d): bf16 A values, B and C once
+                extra[f"spmm_cfg5_{tag}_ms"] = ms5
+                extra[f"spmm_cfg5_{tag}_gbs"] = b5 / (ms5 * 1e-3) / 1e9
+                extra[f"spmm_cfg5_{tag}_tflops"] = 2 * A5.nnz * k5 / (ms5 * 1e-3) / 1e12
+                del A5
+            del B5, C5
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     peak, peak_src = load_peak()
-    for key in ("spmv_banded_gbs", "bicgstab_cfg3_gbs", "spmv_cfg3_gbs", "arnoldi_cfg4_gbs"):
+    for key in ("spmv_banded_gbs", "bicgstab_cfg3_gbs", "spmv_cfg3_gbs", "arnoldi_cfg4_gbs", "spmm_cfg5_k16_gbs", "spmm_cfg5_uniform_gbs"):
         if key in extra:
             extra[key.replace("_gbs", "_frac_per_gpu")] = extra[key] / world / peak
     cpu = None

@@ -166,6 +166,7 @@ sla_status sla_gmres(sla_ctx*, const sla_csr* A, const sla_vec* b, const sla_vec
 typedef enum { SLA_F64 = 0, SLA_BF16 = 1 } sla_dtype;
 sla_status sla_dense_create(sla_ctx*, int64_t rows, int64_t cols, int dtype, sla_dense** out);
 sla_status sla_dense_from_host(sla_ctx*, int64_t rows, int64_t cols, const double* rowmajor, int dtype, sla_dense** out);
+sla_status sla_dense_generate(sla_ctx*, int64_t rows, int64_t cols, uint64_t seed, int dtype, sla_dense** out); /* synthetic, on-device */
 sla_status sla_dense_to_host_f64(sla_ctx*, const sla_dense*, double* rowmajor_out);
 sla_status sla_spmm_dense(sla_ctx*, const sla_csr* A, const sla_dense* B, sla_dense* C);
 

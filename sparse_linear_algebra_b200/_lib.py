@@ -99,6 +99,7 @@ SIGNATURES = {
     "sla_gmres": (C.c_int, [_p, _p, _p, _p, C.c_int, _popts, _p, _pint, _pf64]),
     "sla_dense_create": (C.c_int, [_p, _i64, _i64, C.c_int, _pp]),
     "sla_dense_from_host": (C.c_int, [_p, _i64, _i64, _pf64, C.c_int, _pp]),
+    "sla_dense_generate": (C.c_int, [_p, _i64, _i64, C.c_uint64, C.c_int, _pp]),
     "sla_dense_to_host_f64": (C.c_int, [_p, _p, _pf64]),
     "sla_spmm_dense": (C.c_int, [_p, _p, _p, _p]),
     "sla_dense_dims": (C.c_int, [_p, _pi64, _pi64]),

@@ -271,13 +271,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 #ifndef TC_STAGE
 #define TC_STAGE 2
 #endif
+#define TC_SBO 144              // bytes between core matrices adjacent along M (128 + 16 of padding)
+#define TC_LBO (16 * TC_SBO)    // bytes between the two K halves
 //      // blocks staged (and multiplied) per synchronisation
 
 __global__ void __launch_bounds__(128)
 spmm_bsr_tc_kernel(const int* __restrict__ brow_ptr, const int* __restrict__ bcol, const __nv_bfloat16* __restrict__ bval,
                    const __nv_bfloat16* __restrict__ B, __nv_bfloat16* __restrict__ C, int m, int nbr) {
   __shared__ __align__(128) __nv_bfloat16 sA[TC_STAGE][256];          // 16 x 16 blocks of A (operand B of the MMA)
-  __shared__ __align__(128) __nv_bfloat16 sB[TC_STAGE][16 * 128];     // 16 rows of B each (operand A), canonical MN-major
+  // 16 rows of B each (operand A), canonical MN-major.  The 32 core matrices (8 k-rows x 16 B) are spaced 144 B apart
+  // along M instead of 128 B: the staging stores of 8 lanes (same k, consecutive 8-column groups) then fall into
+  // distinct banks (ncu: with SBO = 128 B they were 8-way conflicts and L1TEX sat at 67 %).
+  __shared__ __align__(128) __nv_bfloat16 sB[TC_STAGE][2 * TC_LBO / 2];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -324,7 +329,7 @@ spmm_bsr_tc_kernel(const int* __restrict__ brow_ptr, const int* __restrict__ bco
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int q = tid + 128 * h, k = q >> 4, mc = q & 15;
-            *reinterpret_cast<uint4*>(sB[j] + mc * 64 + (k >> 3) * 1024 + (k & 7) * 8) = bv[j][h];
+            *reinterpret_cast<uint4*>(sB[j] + mc * (TC_SBO / 2) + (k >> 3) * (TC_LBO / 2) + (k & 7) * 8) = bv[j][h];
           }
         }
       }
@@ -333,7 +338,7 @@ spmm_bsr_tc_kernel(const int* __restrict__ brow_ptr, const int* __restrict__ bco
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int j = 0; j < nb; ++j) {
-          const uint64_t adesc = umma_desc(spmm_smem_u32(sB[j]), 2048, 128);
+          const uint64_t adesc = umma_desc(spmm_smem_u32(sB[j]), TC_LBO, TC_SBO);
           const uint64_t bdesc = umma_desc(spmm_smem_u32(sA[j]), 128, 256);
           const uint32_t acc = (b0 + j) > s ? 1u : 0u;
           asm volatile(
@@ -430,5 +435,25 @@ sla_status sla_spmm_bsr_tc(sla_ctx* c, const sla_csr* A, const sla_dense* B, sla
   spmm_bsr_tc_kernel<<<grid, 128, 0, c->stream>>>(A->bsr_row_ptr, A->bsr_col, (const __nv_bfloat16*)A->bsr_val,
                                                  (const __nv_bfloat16*)B->d, (__nv_bfloat16*)C->d, (int)A->m, A->bsr_nbr);
   SLA_LAUNCH_CHECK(c);
+  return SLA_OK;
+}
+
+// synthetic dense block: entry (r, c) = sla_synth_vec(seed, r * cols + c), rounded to the block's element type
+#include "../../include/sla_synth.h"
+__global__ void dense_synth_kernel(uint64_t seed, int64_t n, double* __restrict__ o64, __nv_bfloat16* __restrict__ o16) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = sla_synth_vec(seed, i);
+    if (o64) o64[i] = v; else o16[i] = __double2bfloat16(v);
+  }
+}
+
+extern "C" sla_status sla_dense_generate(sla_ctx* c, int64_t rows, int64_t cols, uint64_t seed, int dtype, sla_dense** out) {
+  SLA_TRY(sla_dense_create(c, rows, cols, dtype, out));
+  const int64_t n = rows * cols;
+  if (n > 0) {
+    dense_synth_kernel<<<gsb(n), 256, 0, c->stream>>>(seed, n, dtype == SLA_F64 ? (double*)(*out)->d : nullptr,
+                                                     dtype == SLA_BF16 ? (__nv_bfloat16*)(*out)->d : nullptr);
+    SLA_LAUNCH_CHECK(c);
+  }
   return SLA_OK;
 }

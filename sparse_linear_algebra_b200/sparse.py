@@ -311,6 +311,13 @@ class DenseMatrix(DenseBlock):
         return DenseMatrix(ctx, h, dtype)
 
     @staticmethod
+    def generate(rows, cols, seed, dtype=F64, ctx=None):
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        ctx.check(ctx.lib.sla_dense_generate(ctx.h, rows, cols, seed, dtype, C.byref(h)))
+        return DenseMatrix(ctx, h, dtype)
+
+    @staticmethod
     def zeros(rows, cols, dtype=F64, ctx=None):
         ctx = ctx or default_context()
         h = C.c_void_p()
