@@ -275,7 +275,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 #define TC_LBO (16 * TC_SBO)    // bytes between the two K halves
 //      // blocks staged (and multiplied) per synchronisation
 
-__global__ void __launch_bounds__(128)
+#ifndef TC_MINBLOCKS
+#define TC_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, TC_MINBLOCKS)
 spmm_bsr_tc_kernel(const int* __restrict__ brow_ptr, const int* __restrict__ bcol, const __nv_bfloat16* __restrict__ bval,
                    const __nv_bfloat16* __restrict__ B, __nv_bfloat16* __restrict__ C, int m, int nbr) {
   __shared__ __align__(128) __nv_bfloat16 sA[TC_STAGE][256];          // 16 x 16 blocks of A (operand B of the MMA)
