@@ -95,3 +95,30 @@ def test_c_program_runs_on_gpu(lib, tmp_path):
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert "abi_smoke ok" in p.stdout
+
+
+def _build_cpp_mirror(tmp_path):
+    import subprocess
+
+    exe = os.path.join(str(tmp_path), "mirror_smoke")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "mirror_smoke.cpp"),
+                           "-L", os.path.join(ROOT, "sparse_linear_algebra_b200"), "-lsla_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "sparse_linear_algebra_b200"), "-o", exe])
+    return exe
+
+
+def test_cpp_mirror_compiles(lib, tmp_path):
+    """The header-only C++ host mirror (include/sla_b200.hpp) compiles and links; without a GPU it exits 77."""
+    import subprocess
+
+    rc = subprocess.run([_build_cpp_mirror(tmp_path)], capture_output=True, text=True).returncode
+    assert rc in (0, 77)
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_runs_reference_specs_on_gpu(lib, tmp_path):
+    import subprocess
+
+    p = subprocess.run([_build_cpp_mirror(tmp_path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "mirror_smoke ok" in p.stdout
