@@ -241,7 +241,24 @@ def run_gpu(args):
     recv_bytes = 8 * sum(c for d, _, _, c in exchange if d == 0)
 
     extra = {"x_exchange_recv_bytes_per_rank": recv_bytes}
+
+    def sptrsv_extra(tag, M, rhs):
+        """Triangular sweep (triLowerSolve, Sparse.hs:750-777): latency-bound by the number of dependency levels
+        (8191 wavefronts on the 4096^2 grid); single GPU."""
+        t0 = time.perf_counter()
+        lv, nzt = M.triAnalysis(False)
+        ctx.sync()
+        extra[f"sptrsv_{tag}_analysis_ms"] = (time.perf_counter() - t0) * 1e3
+        wv = sla.SpVector.zeroSV(rhs.dim)
+        mst, _ = timed(lambda: sla.triLowerSolve(M, rhs, out=wv), 5, 2)
+        extra[f"sptrsv_{tag}_lower_ms"] = mst
+        extra[f"sptrsv_{tag}_levels"] = lv
+        extra[f"sptrsv_{tag}_us_per_level"] = mst * 1e3 / max(lv, 1)
+        extra[f"sptrsv_{tag}_gbs"] = (12 * nzt + 4 * (rhs.dim + 1) + 16 * rhs.dim) / (mst * 1e-3) / 1e9
+
     if not args.quick:
+        if world == 1:
+            sptrsv_extra("cfg2", A, x)
         del A
         # ---- banded variant of config 2 (columns within +-65536 of the row)
         B = gen(sla.GEN_BANDED, n, k, SEED_CFG2, 65536)
@@ -269,6 +286,8 @@ def run_gpu(args):
         extra["bicgstab_cfg3_launches_per_iter"] = l3 / its
         ms3s, _ = timed(lambda: L3.matVec(xt, out=b), its, 3)
         extra["spmv_cfg3_gbs"] = spmv_bytes(n3, nnz3) / (ms3s * 1e-3) / 1e9
+        if world == 1:
+            sptrsv_extra("cfg3", L3, b)
         del L3, st
         # ---- config 4: arnoldi(A, b, 30) on the random non-symmetric 4M x 4M, 64 nnz/row matrix (row-partitioned)
         n4, k4 = 4_000_000, 64
@@ -307,7 +326,8 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     peak, peak_src = load_peak()
-    for key in ("spmv_banded_gbs", "bicgstab_cfg3_gbs", "spmv_cfg3_gbs", "arnoldi_cfg4_gbs", "spmm_cfg5_k16_gbs", "spmm_cfg5_uniform_gbs"):
+    for key in ("spmv_banded_gbs", "bicgstab_cfg3_gbs", "spmv_cfg3_gbs", "arnoldi_cfg4_gbs", "spmm_cfg5_k16_gbs", "spmm_cfg5_uniform_gbs",
+                "sptrsv_cfg3_gbs", "sptrsv_cfg2_gbs"):
         if key in extra:
             extra[key.replace("_gbs", "_frac_per_gpu")] = extra[key] / world / peak
     cpu = None
@@ -326,7 +346,7 @@ def run_gpu(args):
                    "l2": "no flush: the 3.84 GB matrix stream exceeds the 126 MB L2 every step"},
         "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
                      "traffic": load_traffic(), "peak_source": peak_src, "per_gpu": True,
-                     "kernel": "spmv_tile_kernel<2048, EPI_NONE> (one launch per column panel, 2 panels at n = 10M)"},
+                     "kernel": "spmv_tile_kernel<1024, EPI_NONE> (one launch per column panel, 2 panels at n = 10M)"},
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8 * nloc, "d2h_bytes_per_step": 8 * nloc,
                 "ms_per_step": e2e_s * 1e3, "api": "sla_spmv_host (pinned host buffers, per-rank slices)"},
         "gpu_launches": int(launches),

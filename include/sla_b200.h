@@ -43,7 +43,8 @@ typedef enum {
   SLA_ERR_CUDA = 6,
   SLA_ERR_COMM = 7,
   SLA_ERR_ALLOC = 8,
-  SLA_ERR_INVALID = 9
+  SLA_ERR_INVALID = 9,
+  SLA_ERR_NEEDS_PIVOTING = 10     /* MatrixException NeedsPivoting: a nearZero diagonal in a triangular solve  Control/Exception/Common.hs:57-61, Sparse.hs:757,791 */
 } sla_status;
 
 /* LinSolveMethod  Sparse.hs:1007-1012 (constructor order) */
@@ -169,6 +170,34 @@ sla_status sla_dense_from_host(sla_ctx*, int64_t rows, int64_t cols, const doubl
 sla_status sla_dense_generate(sla_ctx*, int64_t rows, int64_t cols, uint64_t seed, int dtype, sla_dense** out); /* synthetic, on-device */
 sla_status sla_dense_to_host_f64(sla_ctx*, const sla_dense*, double* rowmajor_out);
 sla_status sla_spmm_dense(sla_ctx*, const sla_csr* A, const sla_dense* B, sla_dense* C);
+
+/* ---- preconditioners and triangular solves -------------------------------
+ * Single GPU (a row-partitioned matrix returns SLA_ERR_INVALID).  New matrices are owned by the caller.
+ *
+ * sla_csr_diag_partitions : diagPartitions aa = (extractSubDiag, extractDiag, extractSuperDiag)      Sparse.hs:673-679
+ * sla_jacobi_pre          : jacobiPre x = recip <$> extractDiag x                                   Sparse.hs:686-687
+ * sla_mssor_pre           : mSsorPre aa omega = (l, r),  l = (eye n ^-^ scale omega e) ## reciprocal d,
+ *                           r = d ^-^ scale omega f                                                  Sparse.hs:713-721
+ *     Values are bit-identical to the reference's.  The reference's (##) also stores an explicit 0 for every
+ *     (row, column) pair whose intersection is empty (l has n x n stored entries); those are not materialised.
+ * sla_tri_lower_solve     : triLowerSolve ll b — forward substitution, w_i = (b_i - sum_{j<i asc} l_ij w_j) / l_ii,
+ *                           result passed through sparsifySV (|w_i| <= 1e-12 becomes 0)              Sparse.hs:750-777
+ * sla_tri_upper_solve     : triUpperSolve uu w — backward substitution, x_i = (w_i - sum_{j>i asc} u_ij x_j) / u_ii
+ *                                                                                                   Sparse.hs:784-811
+ *     Only the named triangle and the diagonal of the matrix are read (as in the reference), so a general matrix
+ *     may be passed for a Gauss-Seidel sweep.  Results are bit-identical to the reference's evaluation order.
+ *     A nearZero or missing diagonal entry returns SLA_ERR_NEEDS_PIVOTING (sla_last_error names the row the sweep
+ *     meets first).  A system of dimension 1 returns SLA_ERR_OOB_INDEX: the reference's loop steps before it tests
+ *     and looks up (1,1) resp. (-1,-1) with the bounds-checked `@@` (Iterative.hs:272-282, SpMatrix.hs:108-109).
+ *     The first solve with a matrix builds (and caches in the matrix) a level schedule of its rows.
+ * sla_tri_analysis        : builds that schedule now; reports the number of dependency levels and the stored
+ *                           entries of the triangle including the diagonal (what one solve reads). */
+sla_status sla_csr_diag_partitions(sla_ctx*, const sla_csr* A, sla_csr** E, sla_csr** D, sla_csr** F);
+sla_status sla_jacobi_pre(sla_ctx*, const sla_csr* A, sla_csr** M);
+sla_status sla_mssor_pre(sla_ctx*, const sla_csr* A, double omega, sla_csr** L, sla_csr** R);
+sla_status sla_tri_lower_solve(sla_ctx*, const sla_csr* L, const sla_vec* b, sla_vec* w);
+sla_status sla_tri_upper_solve(sla_ctx*, const sla_csr* U, const sla_vec* w, sla_vec* x);
+sla_status sla_tri_analysis(sla_ctx*, const sla_csr* A, int upper, int* nlevels, int64_t* nnz_tri);
 
 /* ---- dense blocks -------------------------------------------------------------------------- */
 sla_status sla_dense_dims(const sla_dense*, int64_t* rows, int64_t* cols);

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libsla_oracle.so")
 
-ORA_OK, ORA_ERR_SIZE_MISMATCH, ORA_ERR_OOB_INDEX, ORA_ERR_UNSUPPORTED_METHOD = 0, 1, 2, 3
+ORA_OK, ORA_ERR_SIZE_MISMATCH, ORA_ERR_OOB_INDEX, ORA_ERR_UNSUPPORTED_METHOD, ORA_ERR_NEEDS_PIVOTING = 0, 1, 2, 3, 4
 GMRES_, CGNE_, BCG_, CGS_, BICGSTAB_ = 0, 1, 2, 3, 4
 GEN_UNIFORM, GEN_BANDED, GEN_LAPLACE2D, GEN_BLOCK16 = 0, 1, 2, 3
 
@@ -92,6 +92,16 @@ def lib():
         "ora_sm_vecmat": (_p, [_p, _p, _pint]),
         "ora_sm_matmat": (_p, [_p, _p, _pint]),
         "ora_sm_equal": (C.c_int, [_p, _p]),
+        "ora_sm_extract_tri": (_p, [_p, C.c_int]),
+        "ora_sm_eye": (_p, [_i64]),
+        "ora_sm_scale_right": (_p, [_p, _f64]),
+        "ora_sm_negate": (_p, [_p]),
+        "ora_sm_add": (_p, [_p, _p]),
+        "ora_sm_sub": (_p, [_p, _p]),
+        "ora_jacobi_pre": (_p, [_p]),
+        "ora_mssor_pre": (C.c_int, [_p, _f64, C.POINTER(_p), C.POINTER(_p)]),
+        "ora_tri_lower_solve": (_p, [_p, _p, _pint, _pi64]),
+        "ora_tri_upper_solve": (_p, [_p, _p, _pint, _pi64]),
         "ora_krylov_free": (None, [C.POINTER(_Krylov)]),
         "ora_bicgs_init": (C.POINTER(_Krylov), [_p, _p, _p]),
         "ora_bicgstab_step": (C.POINTER(_Krylov), [_p, _p, C.POINTER(_Krylov)]),
@@ -360,6 +370,28 @@ class SpMatrix:
     def __eq__(self, b):
         return bool(lib().ora_sm_equal(self._h, b._h))
 
+    # -- diagonal partitions and matrix arithmetic used by the preconditioners (Sparse.hs:670-721)
+    def extractSubDiag(self):
+        return SpMatrix(lib().ora_sm_extract_tri(self._h, -1))
+
+    def extractDiag(self):
+        return SpMatrix(lib().ora_sm_extract_tri(self._h, 0))
+
+    def extractSuperDiag(self):
+        return SpMatrix(lib().ora_sm_extract_tri(self._h, 1))
+
+    def scale(self, n):        # scale n = fmap (* n)
+        return SpMatrix(lib().ora_sm_scale_right(self._h, float(n)))
+
+    def __add__(self, b):
+        return SpMatrix(lib().ora_sm_add(self._h, b._h))
+
+    def __sub__(self, b):
+        return SpMatrix(lib().ora_sm_sub(self._h, b._h))
+
+    def __neg__(self):
+        return SpMatrix(lib().ora_sm_negate(self._h))
+
 
 class KrylovState:
     """BICGSTAB / CGS / CGNE record (Sparse.hs:855-963). Fields are oracle SpVectors."""
@@ -381,6 +413,48 @@ class KrylovState:
     r = property(lambda s: s._field("r"))
     p = property(lambda s: s._field("p"))
     u = property(lambda s: s._field("u"))
+
+
+class NeedsPivoting(OracleError):
+    """MatrixException NeedsPivoting (Control/Exception/Common.hs:57-61)."""
+
+    def __init__(self, what, row):
+        super().__init__(ORA_ERR_NEEDS_PIVOTING, f"{what} : ({row},{row}) is close to 0")
+        self.row = row
+
+
+def diagPartitions(aa):        # Sparse.hs:673-679
+    return aa.extractSubDiag(), aa.extractDiag(), aa.extractSuperDiag()
+
+
+def jacobiPre(aa):             # Sparse.hs:686-687
+    return SpMatrix(lib().ora_jacobi_pre(aa._h))
+
+
+def mSsorPre(aa, omega):       # Sparse.hs:713-721
+    l, r = _p(), _p()
+    err = lib().ora_mssor_pre(aa._h, float(omega), C.byref(l), C.byref(r))
+    if err:
+        raise OracleError(err, "matMat : incompatible matrix sizes")
+    return SpMatrix(l.value), SpMatrix(r.value)
+
+
+def _tri(fn, what, mm, v):
+    err, bad = C.c_int(0), C.c_int64(-1)
+    h = fn(mm._h, v._h, C.byref(err), C.byref(bad))
+    if err.value == ORA_ERR_NEEDS_PIVOTING:
+        raise NeedsPivoting(what, bad.value)
+    if err.value:
+        raise OracleError(err.value, "@@ : incompatible indices")
+    return SpVector(h)
+
+
+def triLowerSolve(ll, b):      # Sparse.hs:750-777
+    return _tri(lib().ora_tri_lower_solve, "triLowerSolve", ll, b)
+
+
+def triUpperSolve(uu, w):      # Sparse.hs:784-811
+    return _tri(lib().ora_tri_upper_solve, "triUpperSolve", uu, w)
 
 
 def bicgsInit(aa, b, x0):

@@ -436,6 +436,202 @@ int ora_sm_equal(const ora_sm* a, const ora_sm* b) {
   return 1;
 }
 
+/* ------------------------------------------------------------------ preconditioners, triangular solves */
+
+/* filterSM f sm = SM (dim sm) (ifilterIM2 f (dat sm)) ; ifilterIM2 = mapWithKey (\i row -> filterWithKey (f i) row):
+ * inner maps are filtered, every outer row key stays (possibly with an empty inner map).
+ * extractSubDiag / extractDiag / extractSuperDiag keep i > j / i == j / i < j.
+ * SpMatrix.hs:306-315, IntMap2.hs:108-111.   which: -1 sub, 0 diag, +1 super */
+ora_sm* ora_sm_extract_tri(const ora_sm* a, int which) {
+  ora_sm* c = sm_copy(a);
+  for (int64_t r = 0; r < c->nstored; ++r) {
+    ora_sv* row = c->row[r]; int64_t i = c->rkey[r], o = 0;
+    for (int64_t q = 0; q < row->nnz; ++q) {
+      int64_t j = row->idx[q];
+      int keep = which < 0 ? (i > j) : which == 0 ? (i == j) : (i < j);
+      if (keep) { row->idx[o] = j; row->val[o] = row->val[q]; ++o; }
+    }
+    row->nnz = o;
+  }
+  return c;
+}
+
+/* eye n = mkDiagonal n (replicate n 1) = fromListSM (n,n) (zip3 [0..] [0..] ones) ; eye 0 = zeroSM 0 0.  SpMatrix.hs:128-135, 184-191 */
+ora_sm* ora_sm_eye(int64_t n) {
+  ora_sm* a = ora_sm_zero(n, n);
+  for (int64_t i = 0; i < n; ++i) sm_insert(a, i, i, 1.0);
+  return a;
+}
+
+/* scale n = fmap (* n): the scalar is the RIGHT factor.   Class.hs:179-180 */
+ora_sm* ora_sm_scale_right(const ora_sm* a, double n) {
+  ora_sm* c = sm_copy(a);
+  for (int64_t r = 0; r < c->nstored; ++r)
+    for (int64_t q = 0; q < c->row[r]->nnz; ++q) c->row[r]->val[q] = c->row[r]->val[q] * n;
+  return c;
+}
+
+/* negateV = fmap negateV   SpMatrix.hs:79 */
+ora_sm* ora_sm_negate(const ora_sm* a) {
+  ora_sm* c = sm_copy(a);
+  for (int64_t r = 0; r < c->nstored; ++r)
+    for (int64_t q = 0; q < c->row[r]->nnz; ++q) c->row[r]->val[q] = -c->row[r]->val[q];
+  return c;
+}
+
+/* (^+^) = liftU2 (^+^) = SM (maxTup n1 n2) ((liftU2 . liftU2) (+) x1 x2): union of the outer maps,
+ * rows present in both are united entry-wise.   SpMatrix.hs:71-78 */
+ora_sm* ora_sm_add(const ora_sm* a, const ora_sm* b) {
+  ora_sm* c = ora_sm_zero(a->nrows > b->nrows ? a->nrows : b->nrows, a->ncols > b->ncols ? a->ncols : b->ncols);
+  int64_t cap = a->nstored + b->nstored;
+  c->cap = cap;
+  c->rkey = (int64_t*)malloc(sizeof(int64_t) * (size_t)(cap > 0 ? cap : 1));
+  c->row = (ora_sv**)malloc(sizeof(ora_sv*) * (size_t)(cap > 0 ? cap : 1));
+  int64_t i = 0, j = 0, o = 0;
+  while (i < a->nstored || j < b->nstored) {
+    if (j >= b->nstored || (i < a->nstored && a->rkey[i] < b->rkey[j])) { c->rkey[o] = a->rkey[i]; c->row[o] = ora_sv_copy(a->row[i]); ++i; }
+    else if (i >= a->nstored || a->rkey[i] > b->rkey[j])                { c->rkey[o] = b->rkey[j]; c->row[o] = ora_sv_copy(b->row[j]); ++j; }
+    else { c->rkey[o] = a->rkey[i]; c->row[o] = ora_sv_add(a->row[i], b->row[j]); ++i; ++j; }
+    ++o;
+  }
+  c->nstored = o;
+  return c;
+}
+
+/* x ^-^ y = x ^+^ negateV y   Class.hs:68-69 */
+ora_sm* ora_sm_sub(const ora_sm* a, const ora_sm* b) {
+  ora_sm* nb = ora_sm_negate(b);
+  ora_sm* c = ora_sm_add(a, nb);
+  ora_sm_free(nb);
+  return c;
+}
+
+/* jacobiPre x = recip <$> extractDiag x   Sparse.hs:686-687 */
+ora_sm* ora_jacobi_pre(const ora_sm* a) {
+  ora_sm* d = ora_sm_extract_tri(a, 0);
+  ora_sm* c = ora_sm_reciprocal(d);
+  ora_sm_free(d);
+  return c;
+}
+
+/* mSsorPre aa omega = (l, r) where (e, d, f) = diagPartitions aa ; n = nrows e
+ *   l = (eye n ^-^ scale omega e) ## reciprocal d ;  r = d ^-^ scale omega f          Sparse.hs:713-721
+ * NB the (##) stores an entry for EVERY (row of the left factor, stored column of reciprocal d) pair — l has n x n
+ * stored entries, the zeros explicit.  Meant for small n. */
+int ora_mssor_pre(const ora_sm* aa, double omega, ora_sm** l_out, ora_sm** r_out) {
+  ora_sm *e = ora_sm_extract_tri(aa, -1), *d = ora_sm_extract_tri(aa, 0), *f = ora_sm_extract_tri(aa, 1);
+  ora_sm* eye = ora_sm_eye(e->nrows);
+  ora_sm* we = ora_sm_scale_right(e, omega);
+  ora_sm* lhs = ora_sm_sub(eye, we);
+  ora_sm* rd = ora_sm_reciprocal(d);
+  int err = ORA_OK;
+  ora_sm* l = ora_sm_matmat(lhs, rd, &err);
+  ora_sm* wf = ora_sm_scale_right(f, omega);
+  ora_sm* r = ora_sm_sub(d, wf);
+  ora_sm_free(e); ora_sm_free(d); ora_sm_free(f); ora_sm_free(eye); ora_sm_free(we); ora_sm_free(lhs); ora_sm_free(rd); ora_sm_free(wf);
+  if (err != ORA_OK) { ora_sm_free(r); return err; }
+  *l_out = l; *r_out = r;
+  return ORA_OK;
+}
+
+/* m @@ (i, j): bounds-checked lookup with default 0; out of bounds is `error "@@ : incompatible indices"`.
+ * SpMatrix.hs:108-109, 280-287 */
+static int sm_lookup_checked(const ora_sm* a, int64_t i, int64_t j, double* out) {
+  if (!(i >= 0 && i < a->nrows && j >= 0 && j < a->ncols)) return 0;
+  int found; int64_t p = sm_find_row(a, i, &found);
+  *out = 0.0;
+  if (found) { int f2; int64_t q = sv_find(a->row[p], j, &f2); if (f2) *out = a->row[p]->val[q]; }
+  return 1;
+}
+
+static double sv_lookup0(const ora_sv* v, int64_t i) {
+  int found; int64_t q = sv_find(v, i, &found);
+  return found ? v->val[q] : 0.0;
+}
+
+/* extractSubRow m i (j1, j2) `dot` (the matching part of ww): stored entries of row i with j1 <= j <= j2, ascending,
+ * times the entries of the partial solution, which holds EVERY index solved so far (insertSpVector stores zeros too).
+ * Left factor = the matrix entry.   Common.hs:208-216, SpVector.hs:116-117, 350-353 */
+static double subrow_dot(const ora_sm* a, int64_t i, int64_t j1, int64_t j2, const double* ww, int64_t nww) {
+  int found; int64_t p = sm_find_row(a, i, &found);
+  double acc = 0.0;
+  if (!found) return acc;
+  const ora_sv* row = a->row[p];
+  for (int64_t q = 0; q < row->nnz; ++q) {
+    int64_t j = row->idx[q];
+    if (j >= j1 && j <= j2 && j < nww) acc = acc + row->val[q] * ww[j];   /* insertSpVector drops out-of-bounds keys */
+  }
+  return acc;
+}
+
+/* sparsifySV = filterSV isNz   SpVector.hs:390-391 */
+static ora_sv* sv_from_dense_sparsified(int64_t n, const double* w) {
+  ora_sv* v = sv_alloc(n, n);
+  int64_t o = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (!ora_near_zero(w[i])) { v->idx[o] = i; v->val[o] = w[i]; ++o; }
+  v->nnz = o;
+  return v;
+}
+
+/* triLowerSolve ll b (Sparse.hs:750-777):
+ *   lInit: w0 = b0 / l00 (NeedsPivoting when l00 is nearZero) ; state (w, 1)
+ *   lStep (ww, i): lii = ll @@ (i,i) ; wi = (b @@ i - r) / lii, r = extractSubRow ll i (0, i-1) `dot` takeSV i ww
+ *   modifyUntilM' steps FIRST and tests q (_, i) = i == svDim b afterwards (Iterative.hs:272-282): with dim b = 1 the
+ *   first step looks up ll @@ (1,1), which is `error "@@ : incompatible indices"` -> ORA_ERR_OOB_INDEX here.
+ *   result = sparsifySV w.   Entries of ll on or above the diagonal other than lii are never read. */
+ora_sv* ora_tri_lower_solve(const ora_sm* ll, const ora_sv* b, int* err, int64_t* bad_row) {
+  const int64_t nb = b->dim;
+  double lii;
+  if (err) *err = ORA_OK;
+  if (bad_row) *bad_row = -1;
+  if (!sm_lookup_checked(ll, 0, 0, &lii)) { if (err) *err = ORA_ERR_OOB_INDEX; return NULL; }
+  if (ora_near_zero(lii)) { if (err) *err = ORA_ERR_NEEDS_PIVOTING; if (bad_row) *bad_row = 0; return NULL; }
+  double* w = (double*)calloc((size_t)(nb > 0 ? nb : 1), sizeof(double));
+  w[0] = sv_lookup0(b, 0) / lii;
+  int64_t i = 1;
+  for (;;) {
+    if (!sm_lookup_checked(ll, i, i, &lii)) { if (err) *err = ORA_ERR_OOB_INDEX; free(w); return NULL; }
+    if (ora_near_zero(lii)) { if (err) *err = ORA_ERR_NEEDS_PIVOTING; if (bad_row) *bad_row = i; free(w); return NULL; }
+    const double r = subrow_dot(ll, i, 0, i - 1, w, nb);
+    if (i < nb) w[i] = (sv_lookup0(b, i) - r) / lii;
+    ++i;
+    if (i == nb) break;
+  }
+  ora_sv* v = sv_from_dense_sparsified(nb, w);
+  free(w);
+  return v;
+}
+
+/* triUpperSolve uu w (Sparse.hs:784-811): from the last row upwards;
+ *   uInit: i = nw-1 ; x_i = w_i / (uu @@! (i,i))  (unchecked lookup; NeedsPivoting reports index 0 there, :802)
+ *   uStep (xx, i): uii = uu @@ (i,i) ; xi = (w @@ i - r) / uii, r = extractSubRow_RK uu i (i+1, nw-1) `dot` dropSV (i+1) xx
+ *   stops when i == -1 AFTER a step: nw = 1 looks up uu @@ (-1,-1) -> ORA_ERR_OOB_INDEX. */
+ora_sv* ora_tri_upper_solve(const ora_sm* uu, const ora_sv* wv, int* err, int64_t* bad_row) {
+  const int64_t nw = wv->dim;
+  if (err) *err = ORA_OK;
+  if (bad_row) *bad_row = -1;
+  if (nw < 1) { if (err) *err = ORA_ERR_OOB_INDEX; return NULL; }
+  double uii = 0.0;
+  { int found; int64_t p = sm_find_row(uu, nw - 1, &found);          /* (@@!) = lookupWD_SM: default 0, no bounds check */
+    if (found) { int f2; int64_t q = sv_find(uu->row[p], nw - 1, &f2); if (f2) uii = uu->row[p]->val[q]; } }
+  if (ora_near_zero(uii)) { if (err) *err = ORA_ERR_NEEDS_PIVOTING; if (bad_row) *bad_row = nw - 1; return NULL; }
+  double* x = (double*)calloc((size_t)nw, sizeof(double));
+  x[nw - 1] = sv_lookup0(wv, nw - 1) / uii;
+  int64_t i = nw - 2;
+  for (;;) {
+    if (!sm_lookup_checked(uu, i, i, &uii)) { if (err) *err = ORA_ERR_OOB_INDEX; free(x); return NULL; }
+    if (ora_near_zero(uii)) { if (err) *err = ORA_ERR_NEEDS_PIVOTING; if (bad_row) *bad_row = i; free(x); return NULL; }
+    const double r = subrow_dot(uu, i, i + 1, nw - 1, x, nw);
+    if (i >= 0) x[i] = (sv_lookup0(wv, i) - r) / uii;
+    --i;
+    if (i == -1) break;
+  }
+  ora_sv* v = sv_from_dense_sparsified(nw, x);
+  free(x);
+  return v;
+}
+
 /* ------------------------------------------------------------------ Krylov */
 
 static ora_krylov* kry_new(ora_sv* x, ora_sv* r, ora_sv* p, ora_sv* u) {

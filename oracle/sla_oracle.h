@@ -33,7 +33,8 @@ typedef struct ora_sv { int64_t dim, nnz, cap; int64_t* idx; double* val; } ora_
 /* SpMatrix a = SM (rows, cols) (IntM (IntM a))   src/Data/Sparse/SpMatrix.hs:52-54 */
 typedef struct ora_sm { int64_t nrows, ncols, nstored, cap; int64_t* rkey; ora_sv** row; } ora_sm;
 
-enum { ORA_OK = 0, ORA_ERR_SIZE_MISMATCH = 1, ORA_ERR_OOB_INDEX = 2, ORA_ERR_UNSUPPORTED_METHOD = 3 };
+enum { ORA_OK = 0, ORA_ERR_SIZE_MISMATCH = 1, ORA_ERR_OOB_INDEX = 2, ORA_ERR_UNSUPPORTED_METHOD = 3,
+       ORA_ERR_NEEDS_PIVOTING = 4 /* MatrixException NeedsPivoting, Control/Exception/Common.hs:57-61 */ };
 /* LinSolveMethod, Sparse.hs:1007-1012 */
 enum { ORA_GMRES = 0, ORA_CGNE = 1, ORA_BCG = 2, ORA_CGS = 3, ORA_BICGSTAB = 4 };
 
@@ -79,6 +80,20 @@ ora_sv* ora_sm_matvec(const ora_sm* a, const ora_sv* x, int* err);        /* (#>
 ora_sv* ora_sm_vecmat(const ora_sv* x, const ora_sm* a, int* err);        /* (<#) vecMatSD  Common.hs:253-256 */
 ora_sm* ora_sm_matmat(const ora_sm* a, const ora_sm* b, int* err);        /* (##)  SpMatrix.hs:768-811 */
 int     ora_sm_equal(const ora_sm* a, const ora_sm* b);                   /* derived Eq */
+
+/* ---- preconditioners and triangular solves (Sparse.hs:670-811) ---- */
+ora_sm* ora_sm_extract_tri(const ora_sm* a, int which);                   /* extractSubDiag (-1) / extractDiag (0) / extractSuperDiag (+1)  SpMatrix.hs:306-315 */
+ora_sm* ora_sm_eye(int64_t n);                                            /* eye               SpMatrix.hs:128-135 */
+ora_sm* ora_sm_scale_right(const ora_sm* a, double n);                    /* scale n = fmap (* n)  Class.hs:179-180 */
+ora_sm* ora_sm_negate(const ora_sm* a);                                   /* negateV           SpMatrix.hs:79 */
+ora_sm* ora_sm_add(const ora_sm* a, const ora_sm* b);                     /* (^+^)             SpMatrix.hs:71-78 */
+ora_sm* ora_sm_sub(const ora_sm* a, const ora_sm* b);                     /* (^-^)     Class.hs:68-69 */
+ora_sm* ora_jacobi_pre(const ora_sm* a);                                  /* jacobiPre         Sparse.hs:686-687 */
+int     ora_mssor_pre(const ora_sm* aa, double omega, ora_sm** l, ora_sm** r); /* mSsorPre     Sparse.hs:713-721 */
+/* *err: ORA_ERR_NEEDS_PIVOTING (with *bad_row = the row whose diagonal is nearZero) or ORA_ERR_OOB_INDEX (the
+ * `@@` lookup past the matrix that a system of dimension 1 runs into). */
+ora_sv* ora_tri_lower_solve(const ora_sm* ll, const ora_sv* b, int* err, int64_t* bad_row);  /* triLowerSolve Sparse.hs:750-777 */
+ora_sv* ora_tri_upper_solve(const ora_sm* uu, const ora_sv* w, int* err, int64_t* bad_row);  /* triUpperSolve Sparse.hs:784-811 */
 
 /* ---- Krylov states (Sparse.hs:855-981) ---- */
 typedef struct { ora_sv *x, *r, *p, *u; } ora_krylov;   /* BICGSTAB: x r p; CGS: x r p u; CGNE: x r p */

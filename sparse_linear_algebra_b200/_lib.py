@@ -11,11 +11,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLA_LIB_PATH") or os.path.join(_HERE, "libsla_b200.so")   # SLA_LIB_PATH: tuning experiments only
 
 (SLA_OK, SLA_ERR_SIZE_MISMATCH, SLA_ERR_OOB_INDEX, SLA_ERR_UNSUPPORTED_METHOD, SLA_ERR_NOT_CONVERGED,
- SLA_ERR_BREAKDOWN, SLA_ERR_CUDA, SLA_ERR_COMM, SLA_ERR_ALLOC, SLA_ERR_INVALID) = range(10)
+ SLA_ERR_BREAKDOWN, SLA_ERR_CUDA, SLA_ERR_COMM, SLA_ERR_ALLOC, SLA_ERR_INVALID, SLA_ERR_NEEDS_PIVOTING) = range(11)
 
 STATUS_NAMES = ["SLA_OK", "SLA_ERR_SIZE_MISMATCH", "SLA_ERR_OOB_INDEX", "SLA_ERR_UNSUPPORTED_METHOD",
                 "SLA_ERR_NOT_CONVERGED", "SLA_ERR_BREAKDOWN", "SLA_ERR_CUDA", "SLA_ERR_COMM", "SLA_ERR_ALLOC",
-                "SLA_ERR_INVALID"]
+                "SLA_ERR_INVALID", "SLA_ERR_NEEDS_PIVOTING"]
 
 
 class SolveOpts(C.Structure):
@@ -102,6 +102,12 @@ SIGNATURES = {
     "sla_dense_generate": (C.c_int, [_p, _i64, _i64, C.c_uint64, C.c_int, _pp]),
     "sla_dense_to_host_f64": (C.c_int, [_p, _p, _pf64]),
     "sla_spmm_dense": (C.c_int, [_p, _p, _p, _p]),
+    "sla_csr_diag_partitions": (C.c_int, [_p, _p, _pp, _pp, _pp]),
+    "sla_jacobi_pre": (C.c_int, [_p, _p, _pp]),
+    "sla_mssor_pre": (C.c_int, [_p, _p, _f64, _pp, _pp]),
+    "sla_tri_lower_solve": (C.c_int, [_p, _p, _p, _p]),
+    "sla_tri_upper_solve": (C.c_int, [_p, _p, _p, _p]),
+    "sla_tri_analysis": (C.c_int, [_p, _p, C.c_int, _pint, _pi64]),
     "sla_dense_dims": (C.c_int, [_p, _pi64, _pi64]),
     "sla_dense_to_host": (C.c_int, [_p, _p, _pf64]),
     "sla_dense_free": (None, [_p]),

@@ -93,6 +93,9 @@ struct sla_csr {
   void* val_bf16;            // bf16 copy of val for the bf16 (##) path, built on first use (spmm.cu)
   int bsr_ready, bsr_nbr, bsr_nblk; int *bsr_row_ptr, *bsr_col; void* bsr_val;   // 16 x 16 bf16 block copy for the tcgen05 (##) path
   int chunk_ready, chunk_tile[8], chunk_row[8];   // row chunks of the last pass for the pipelined host (#>)
+  // triangular solves (trisolve.cu): level schedules [0] forward / [1] backward, position of the diagonal in every row,
+  // the polled partial solution and the chunk ticket
+  void* tri[2]; int32_t* tri_diag; double* tri_w; unsigned int* tri_ticket;
 };
 
 // dimension a vector must have to be multiplied by A / to receive A's product, on this rank
@@ -278,6 +281,7 @@ sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P);                 
 sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count);
 void sla_csr_free_dist(sla_csr* A);
 void sla_csr_free_bsr(sla_csr* A);
+void sla_csr_free_tri(sla_csr* A);                                                                // trisolve.cu
 static inline int fin_for(const sla_ctx* c, int fin) { return c->world > 1 ? (fin | FIN_DEFER) : fin; }
 
 // SpMV epilogues

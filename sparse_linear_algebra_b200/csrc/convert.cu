@@ -49,6 +49,7 @@ extern "C" void sla_csr_free(sla_csr* A) {
   sla_csr_free_panels(A);
   sla_csr_free_dist(A);
   sla_csr_free_bsr(A);
+  sla_csr_free_tri(A);
   cudaFree(A->row_ptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->tile_row); cudaFree(A->val_bf16);
   delete A;
 }

@@ -54,8 +54,12 @@ class IterE(SlaError):
     """IterationException IterE (Control/Exception/Common.hs:67-76), e.g. unsupported linSolve0 method."""
 
 
+class NeedsPivoting(SlaError):
+    """MatrixException NeedsPivoting: a nearZero diagonal met by a triangular solve (Control/Exception/Common.hs:57-61)."""
+
+
 _ERR_CLASS = {L.SLA_ERR_SIZE_MISMATCH: MatVecSizeMismatchException, L.SLA_ERR_OOB_INDEX: OutOfBoundsIndexError,
-              L.SLA_ERR_UNSUPPORTED_METHOD: IterE}
+              L.SLA_ERR_UNSUPPORTED_METHOD: IterE, L.SLA_ERR_NEEDS_PIVOTING: NeedsPivoting}
 
 
 class Context:
@@ -464,6 +468,27 @@ class SpMatrix:
         self.ctx.check(self.ctx.lib.sla_spmv_host(self.ctx.h, self.h, xp, y.ctypes.data_as(C.POINTER(C.c_double))))
         return y
 
+    # -- diagonal partitions (SpMatrix.hs:306-315) and the schedule of the triangular solves
+    def _parts(self):
+        e, d, f = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.ctx.check(self.ctx.lib.sla_csr_diag_partitions(self.ctx.h, self.h, C.byref(e), C.byref(d), C.byref(f)))
+        return SpMatrix(self.ctx, e), SpMatrix(self.ctx, d), SpMatrix(self.ctx, f)
+
+    def extractSubDiag(self):
+        return self._parts()[0]
+
+    def extractDiag(self):
+        return self._parts()[1]
+
+    def extractSuperDiag(self):
+        return self._parts()[2]
+
+    def triAnalysis(self, upper=False):
+        """(dependency levels, stored entries of the triangle incl. the diagonal) of the cached level schedule."""
+        lv, nz = C.c_int(0), C.c_int64(0)
+        self.ctx.check(self.ctx.lib.sla_tri_analysis(self.ctx.h, self.h, 1 if upper else 0, C.byref(lv), C.byref(nz)))
+        return lv.value, nz.value
+
     def matMat(self, b, out=None):        # aa ## b, b a dense row-major block
         cc = out if out is not None else DenseMatrix.zeros(self.nrows, b.dim[1], b.dtype, self.ctx)
         self.ctx.check(self.ctx.lib.sla_spmm_dense(self.ctx.h, self.h, b.h, cc.h))
@@ -587,6 +612,39 @@ def gmres(aa, b, x0, restart=30, nits=0, tol_abs=0.0, tol_rel=0.0, info=False):
     iters, res = C.c_int(0), C.c_double(0)
     ctx.check(ctx.lib.sla_gmres(ctx.h, aa.h, b.h, x0.h, restart, C.byref(o), x.h, C.byref(iters), C.byref(res)))
     return (x, iters.value, res.value) if info else x
+
+
+def diagPartitions(aa):
+    """diagPartitions aa = (e, d, f): strictly sub-diagonal, diagonal, strictly super-diagonal parts (Sparse.hs:673-679)."""
+    return aa._parts()
+
+
+def jacobiPre(aa):
+    """jacobiPre x = recip <$> extractDiag x (Sparse.hs:686-687)."""
+    h = C.c_void_p()
+    aa.ctx.check(aa.ctx.lib.sla_jacobi_pre(aa.ctx.h, aa.h, C.byref(h)))
+    return SpMatrix(aa.ctx, h)
+
+
+def mSsorPre(aa, omega):
+    """mSsorPre aa omega = (l, r), l = (eye n ^-^ scale omega e) ## reciprocal d, r = d ^-^ scale omega f (Sparse.hs:713-721)."""
+    l, r = C.c_void_p(), C.c_void_p()
+    aa.ctx.check(aa.ctx.lib.sla_mssor_pre(aa.ctx.h, aa.h, float(omega), C.byref(l), C.byref(r)))
+    return SpMatrix(aa.ctx, l), SpMatrix(aa.ctx, r)
+
+
+def triLowerSolve(ll, b, out=None):
+    """triLowerSolve ll b: forward substitution (Sparse.hs:750-777); raises NeedsPivoting on a nearZero diagonal."""
+    w = out if out is not None else SpVector.zeroSV(b.dim, ll.ctx)
+    ll.ctx.check(ll.ctx.lib.sla_tri_lower_solve(ll.ctx.h, ll.h, b.h, w.h))
+    return w
+
+
+def triUpperSolve(uu, w, out=None):
+    """triUpperSolve uu w: backward substitution (Sparse.hs:784-811)."""
+    x = out if out is not None else SpVector.zeroSV(w.dim, uu.ctx)
+    uu.ctx.check(uu.ctx.lib.sla_tri_upper_solve(uu.ctx.h, uu.h, w.h, x.h))
+    return x
 
 
 def backslash(aa, b):

@@ -33,8 +33,15 @@ def main():
     cases = [("uniform", sla.GEN_UNIFORM, ora.GEN_UNIFORM, 20000, 16, 0),
              ("banded", sla.GEN_BANDED, ora.GEN_BANDED, 30000, 16, 300),
              ("laplace", sla.GEN_LAPLACE2D, ora.GEN_LAPLACE2D, 96 * 96, 5, 96),
-             ("ragged", sla.GEN_UNIFORM, ora.GEN_UNIFORM, 1001, 8, 0)]
+             ("ragged", sla.GEN_UNIFORM, ora.GEN_UNIFORM, 1001, 8, 0),
+             ("uniform-panels", sla.GEN_UNIFORM, ora.GEN_UNIFORM, 24000, 12, 0)]
     for name, gk, ok_, n, k, band in cases:
+        # the column-panel plan is chosen when the matrix is built: force 3 panels for the last case so the
+        # row-partitioned kernel's panel continuation is covered at a size the oracle checks in full
+        if name.endswith("panels"):
+            os.environ["SLA_SPMV_PANELS"] = "3"
+        else:
+            os.environ.pop("SLA_SPMV_PANELS", None)
         A = sd.generate_distributed(ctx, gk, n, k, seed, band)
         starts = A.row_starts
         r0, r1 = starts[rank], starts[rank + 1]

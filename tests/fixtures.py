@@ -45,3 +45,15 @@ def tm7_triples():
     t += [(i, i, 2.0) for i in range(n)]
     t += [(i + 1, i, -1.0) for i in range(n - 1)]
     return (n, n), t
+
+# triangular-solve fixtures, LibSpec.hs:1409-1434 (the reference checks them through the residual, :436-459;
+# the "#>" comments beside ltri1 there do not match its right-hand side, the residual test still passes)
+LTRI0 = ((2, 2), [(0, 0, 2), (1, 0, 1), (1, 1, 3)])
+B_LTRI0 = [4, 11]
+UTRI0 = ((2, 2), [(0, 0, 2), (0, 1, 1), (1, 1, 3)])
+B_UTRI0 = [7, 9]
+LTRI1 = ((3, 3), [(0, 0, 2), (1, 0, 1), (1, 1, 4), (2, 1, 2), (2, 2, 3)])
+B_LTRI1 = [4, 10, 17]
+UTRI1 = ((3, 3), [(0, 0, 2), (0, 1, 1), (0, 2, 1), (1, 1, 4), (1, 2, 2), (2, 2, 3)])
+B_UTRI1 = [9, 14, 9]
+TRI_SPECS = [("lower", LTRI0, B_LTRI0), ("upper", UTRI0, B_UTRI0), ("lower", LTRI1, B_LTRI1), ("upper", UTRI1, B_UTRI1)]

@@ -434,6 +434,46 @@ def test_gmres_converges(sla, o):
     np.testing.assert_allclose(x.toDenseListSV(), xt.toDenseListSV(), atol=1e-8)
 
 
+def test_gmres_restarts_and_solver_options(sla, o):
+    """GMRES with a short restart length needs several cycles; linSolve0's check_every / recurrence-residual
+    options change when the loop looks, not what it computes."""
+    n, k, seed = 3000, 12, 0x5EED0007
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+    xt = sla.SpVector.generate(n, seed + 2)
+    b = A @ xt
+    x, it, res = sla.gmres(A, b, sla.SpVector.zeroSV(n), restart=3, tol_abs=1e-10, tol_rel=1e-12, info=True)
+    assert it > 3 and res <= 1e-9 * b.norm2() + 1e-10
+    np.testing.assert_allclose(x.toDenseListSV(), xt.toDenseListSV(), atol=1e-8)
+    x0 = sla.SpVector.constv(n, 0.1)
+    xa, ita, _ = sla.linSolve0(sla.BICGSTAB_, A, b, x0, info=True)
+    xb, itb, resb = sla.linSolve0(sla.BICGSTAB_, A, b, x0, check_every=3, info=True)
+    assert itb >= ita and itb % 3 == 0 and itb - ita < 3
+    xc, itc, resc = sla.linSolve0(sla.BICGSTAB_, A, b, x0, true_residual=False, info=True)
+    assert abs(itc - ita) <= 1
+    tol = max(1e-6, 1e-4 * (b - (A @ x0)).norm2())
+    for xs in (xa, xb, xc):
+        assert ((A @ xs) - b).norm2() <= 1.01 * tol
+
+
+def test_csr_input_validation(sla, o):
+    """sla_csr_from_csr: already-CSR input is accepted as is (bit-exact product) and validated."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(60)
+    S = sp.random(300, 200, density=0.05, random_state=60, format="csr", dtype=np.float64)
+    S.sort_indices()
+    A = sla.SpMatrix.fromCSR(300, 200, S.indptr, S.indices, S.data)
+    x = rng.standard_normal(200)
+    Ao = o.SpMatrix.fromCSR(300, 200, S.indptr, S.indices, S.data)
+    assert (A @ sla.SpVector.mkSpVR(200, x)).toDenseListSV().tobytes() == Ao.matVec(o.SpVector.mkSpVR(200, x)).toDenseListSV().tobytes()
+    with pytest.raises(sla.SlaError):                    # columns not ascending
+        sla.SpMatrix.fromCSR(1, 3, [0, 2], [2, 0], [1.0, 2.0])
+    with pytest.raises(sla.OutOfBoundsIndexError):       # column out of range
+        sla.SpMatrix.fromCSR(1, 3, [0, 1], [3], [1.0])
+    with pytest.raises(sla.SlaError):                    # row_ptr does not end at nnz
+        sla.SpMatrix.fromCSR(2, 3, [0, 1, 1], [0, 1], [1.0, 2.0])
+
+
 # =============================================================== (##) with a dense right operand
 
 def _bf16_round(a):
