@@ -243,6 +243,14 @@ def run_gpu(args):
     extra = {"x_exchange_recv_bytes_per_rank": recv_bytes}
 
     def sptrsv_extra(tag, M, rhs):
+        if args.no_sptrsv:
+            return
+        try:
+            _sptrsv_extra(tag, M, rhs)
+        except Exception as e:                     # context numbers only: never lose the headline line
+            extra[f"sptrsv_{tag}_error"] = str(e)[:200]
+
+    def _sptrsv_extra(tag, M, rhs):
         """Triangular sweep (triLowerSolve, Sparse.hs:750-777): latency-bound by the number of dependency levels
         (8191 wavefronts on the 4096^2 grid); single GPU."""
         t0 = time.perf_counter()
@@ -367,6 +375,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip the banded / BiCGSTAB context runs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sptrsv", action="store_true", help="skip the triangular-sweep context numbers")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -1,4 +1,5 @@
-"""Times the triangular sweeps (analysis + solve) on the cfg3 Laplacian and the cfg2 uniform matrix.  GPU only."""
+"""Times the triangular sweeps (analysis + solve) on the cfg3 Laplacian and the cfg2 uniform matrix.  GPU only.
+usage: bench_sptrsv.py [cfg3|cfg2|banded ...]   (default: all three)"""
 import json
 import sys
 import time
@@ -8,8 +9,11 @@ import sparse_linear_algebra_b200 as sla
 
 ctx = sla.default_context()
 out = {}
+want = set(sys.argv[1:])
 for tag, kind, n, k, band in (("cfg3", sla.GEN_LAPLACE2D, 4096 * 4096, 5, 4096), ("cfg2", sla.GEN_UNIFORM, 10_000_000, 32, 0),
                               ("banded", sla.GEN_BANDED, 10_000_000, 32, 65536)):
+    if want and tag not in want:
+        continue
     A = sla.SpMatrix.generate(kind, n, k, 0x5EED0002, band)
     b = sla.SpVector.generate(n, 7)
     w = sla.SpVector.zeroSV(n)
