@@ -240,7 +240,9 @@ def run_gpu(args):
     exchange = getattr(A, "dist_plan", [])
     recv_bytes = 8 * sum(c for d, _, _, c in exchange if d == 0)
 
-    extra = {"x_exchange_recv_bytes_per_rank": recv_bytes}
+    p2p = bool(getattr(ctx, "p2p", False)) and bool(getattr(A, "dist_p2p", False))
+    extra = {"x_exchange_recv_bytes_per_rank": recv_bytes,
+             "collectives": ("peer-memory kernels over NVLink (csrc/p2p.cu)" if p2p else "nccl") if world > 1 else "none"}
 
     def sptrsv_extra(tag, M, rhs):
         if args.no_sptrsv:
@@ -264,16 +266,20 @@ def run_gpu(args):
         extra[f"sptrsv_{tag}_us_per_level"] = mst * 1e3 / max(lv, 1)
         extra[f"sptrsv_{tag}_gbs"] = (12 * nzt + 4 * (rhs.dim + 1) + 16 * rhs.dim) / (mst * 1e-3) / 1e9
 
-    if not args.quick:
-        if world == 1:
-            sptrsv_extra("cfg2", A, x)
-        del A
+    want = set() if args.quick else set(args.extras.split(","))
+    if args.no_sptrsv:
+        want.discard("sptrsv")
+    if "sptrsv" in want and world == 1:
+        sptrsv_extra("cfg2", A, x)
+    del A
+    if "banded" in want:
         # ---- banded variant of config 2 (columns within +-65536 of the row)
         B = gen(sla.GEN_BANDED, n, k, SEED_CFG2, 65536)
         msb, _ = timed(lambda: B.matVec(x, out=y), args.steps, args.warmup)
         extra["spmv_banded_gbs"] = nbytes / (msb * 1e-3) / 1e9
         extra["spmv_banded_ms"] = msb
         del B
+    if "cfg3" in want:
         # ---- config 3: BiCGSTAB on the 5-point Laplacian 4096^2, fixed number of bicgstabStep calls
         g = G_CFG3
         n3 = g * g
@@ -294,9 +300,10 @@ def run_gpu(args):
         extra["bicgstab_cfg3_launches_per_iter"] = l3 / its
         ms3s, _ = timed(lambda: L3.matVec(xt, out=b), its, 3)
         extra["spmv_cfg3_gbs"] = spmv_bytes(n3, nnz3) / (ms3s * 1e-3) / 1e9
-        if world == 1:
+        if world == 1 and "sptrsv" in want:
             sptrsv_extra("cfg3", L3, b)
         del L3, st
+    if "cfg4" in want:
         # ---- config 4: arnoldi(A, b, 30) on the random non-symmetric 4M x 4M, 64 nnz/row matrix (row-partitioned)
         n4, k4 = 4_000_000, 64
         A4 = gen(sla.GEN_UNIFORM, n4, k4, 0x5EED0004)
@@ -312,6 +319,7 @@ def run_gpu(args):
         extra["arnoldi_cfg4_ms_per_cycle"] = s4 * 1e3
         extra["arnoldi_cfg4_gbs"] = b4bytes / s4 / 1e9
         del A4, Qd
+    if "cfg5" in want:
         # ---- config 5: (##) CSR 10M x 10M x dense 10M x 128 bf16 (single GPU: ## is not row-partitioned yet).
         # K16 = block-structured family (tcgen05 tile path); U = uniform columns (gather kernel, L2-bound).
         if world == 1:
@@ -349,7 +357,7 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg2: CSR SpMV (#>) fp64, 10M x 10M, 32 nnz/row, uniform columns"
-                               + (f", row-partitioned over {world} B200 (x all-gathered every step)" if world > 1 else ", 1 x B200"),
+                               + (f", row-partitioned over {world} B200 (remote x blocks exchanged every step)" if world > 1 else ", 1 x B200"),
                    "n": n, "nnz": n * k, "algorithmic_bytes_per_step": nbytes,
                    "l2": "no flush: the 3.84 GB matrix stream exceeds the 126 MB L2 every step"},
         "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
@@ -374,6 +382,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip the banded / BiCGSTAB context runs")
+    ap.add_argument("--extras", default="sptrsv,banded,cfg3,cfg4,cfg5",
+                    help="comma list of the context runs to include (sptrsv, banded, cfg3, cfg4, cfg5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sptrsv", action="store_true", help="skip the triangular-sweep context numbers")
     args = ap.parse_args()

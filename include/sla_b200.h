@@ -91,6 +91,18 @@ sla_status sla_csr_generate_rows(sla_ctx*, int kind, int64_t n, int nnz_per_row,
 sla_status sla_csr_col_range(sla_ctx*, const sla_csr*, int64_t* lo, int64_t* hi);   /* hi < lo: no entries */
 sla_status sla_csr_set_dist(sla_ctx*, sla_csr*, int64_t row0, int nseg, const int* dir, const int* peer,
                             const int64_t* goff, const int64_t* count, int allgather /* same value on EVERY rank */);
+/* Peer-memory collectives over NVLink / NVSwitch (csrc/p2p.cu): the all-reduce behind every dot and the x exchange
+ * before a row-partitioned (#>) run as single kernels that store straight into the peers' windows instead of
+ * calling NCCL.  Set-up is host plumbing: every rank exports a 64-byte cudaIpcMemHandle_t, the host gathers the
+ * `world` handles in rank order, every rank attaches, and the switch is thrown with the SAME value on every rank
+ * (on = every rank exported and attached).  Context first, then each distributed matrix after sla_csr_set_dist. */
+sla_status sla_p2p_export(sla_ctx*, void* handle64);
+sla_status sla_p2p_attach(sla_ctx*, const void* handles /* world x 64 bytes */);
+sla_status sla_p2p_enable(sla_ctx*, int on);
+int        sla_p2p_enabled(const sla_ctx*);
+sla_status sla_csr_p2p_export(sla_ctx*, sla_csr*, void* handle64);
+sla_status sla_csr_p2p_attach(sla_ctx*, sla_csr*, const void* handles /* world x 64 bytes */);
+sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on);
 sla_status sla_vec_generate_slice(sla_ctx*, int64_t i0, int64_t n, uint64_t seed, sla_vec** out);
 sla_status sla_csr_dims(const sla_csr*, int64_t* m, int64_t* n, int64_t* nnz);
 sla_status sla_csr_to_host(sla_ctx*, const sla_csr*, int32_t* row_ptr, int32_t* col_idx, double* val);

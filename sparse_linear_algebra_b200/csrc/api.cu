@@ -69,6 +69,9 @@ extern "C" void sla_finalize(sla_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  sla_p2p_free(c);
+  for (int k = 0; k < c->n_parked; ++k) cudaFree(c->parked[k]);
+  c->n_parked = 0;
   if (c->nccl) sla_dist_detach(c);
   sla_vec_free(c->scratch_x); sla_vec_free(c->scratch_y); sla_vec_free(c->scratch_r);
   if (c->copy_stream) {
@@ -84,7 +87,7 @@ extern "C" void sla_finalize(sla_ctx* c) {
 extern "C" sla_status sla_sync(sla_ctx* c) {
   if (!c) return SLA_ERR_INVALID;
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));
-  return SLA_OK;
+  return sla_p2p_check(c);            // a timed-out peer wait surfaces here as SLA_ERR_COMM
 }
 extern "C" void* sla_stream(sla_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" int sla_rank(const sla_ctx* c) { return c ? c->rank : 0; }
@@ -120,7 +123,7 @@ sla_status sla_read_scalars(sla_ctx* c, int first, int count, double* host_out) 
                               cudaMemcpyDeviceToHost, c->stream));
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int k = 0; k < count; ++k) host_out[k] = c->h_scal[first + k];
-  return SLA_OK;
+  return c->world > 1 ? sla_p2p_check(c) : SLA_OK;
 }
 
 // ---- vectors --------------------------------------------------------------------------------------

@@ -13,6 +13,8 @@
 #define SLA_MAX_KRYLOV 384       // max Arnoldi / GMRES basis size (H column lives in scal[S_HCOL..])
 #define SLA_MAX_PARTIALS (1 << 20)
 #define SLA_MAX_PANELS 64        // column panels per matrix (spmv.cu)
+#define SLA_MAX_WORLD 16         // ranks of one NVSwitch domain the peer-memory collectives address (p2p.cu)
+#define SLA_MAX_PARKED 256       // retired peer-memory windows kept until sla_finalize (p2p.cu)
 
 // device scalar slots (doubles living in ctx->scal)
 enum {
@@ -43,6 +45,8 @@ struct sla_ctx {
   cudaEvent_t ev_copy[SLA_MAX_PANELS + 16];
   int spmv_tma;              // 0: LDG tile kernel; k > 0: TMA-staged persistent kernel with k CTAs per SM (env SLA_SPMV_TMA)
   const void* scal_owner;    // Krylov state whose recurrence scalars currently live in scal[]
+  struct sla_p2p* p2p;       // peer-memory all-reduce window (p2p.cu); null / disabled: NCCL
+  void* parked[SLA_MAX_PARKED]; int n_parked;   // exchange windows of freed matrices (peers may still map them)
   char err[512];
 };
 
@@ -72,6 +76,7 @@ struct sla_dist_info {
   int pipelined;
   int pan_first[SLA_MAX_PANELS + 1];   // pseg[pan_first[p] .. pan_first[p+1]) belong to panel p
   sla_xseg* pseg;
+  struct sla_xwin* xwin;     // peer-memory exchange window (p2p.cu); when enabled xfull points into it
 };
 
 struct sla_csr {
@@ -280,6 +285,14 @@ sla_status sla_dist_exchange_panel(sla_ctx* c, const sla_csr* A, const double* x
 sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P);                                   // spmv.cu
 sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count);
 void sla_csr_free_dist(sla_csr* A);
+// peer-memory collectives (p2p.cu)
+bool sla_p2p_active(const sla_ctx* c);
+sla_status sla_p2p_allreduce(sla_ctx* c, int nv, int src, int fin, int dst);
+sla_status sla_p2p_check(sla_ctx* c);
+void sla_p2p_free(sla_ctx* c);
+bool sla_xwin_active(const sla_csr* A);
+sla_status sla_p2p_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local);
+void sla_xwin_free(sla_csr* A);
 void sla_csr_free_bsr(sla_csr* A);
 void sla_csr_free_tri(sla_csr* A);                                                                // trisolve.cu
 static inline int fin_for(const sla_ctx* c, int fin) { return c->world > 1 ? (fin | FIN_DEFER) : fin; }

@@ -121,6 +121,8 @@ __global__ void finalize_kernel(int fin, int dst, double* scal, int src, int nv)
 // Completes a reduction whose per-rank sums sit in scal[S_RAW .. S_RAW + nv): all-reduce, then finalize.
 sla_status sla_dist_finish_reduction(sla_ctx* c, int nv, int fin, int dst) {
   if (c->world <= 1) return SLA_OK;
+  // peer-memory path: all-reduce + post-processing in ONE single-CTA kernel (p2p.cu)
+  if (sla_p2p_active(c) && nv <= 8) return sla_p2p_allreduce(c, nv, fin == FIN_STORE ? dst : S_RAW, fin, dst);
   ncclComm_t comm = (ncclComm_t)c->nccl;
   if (fin == FIN_STORE) {
     // raw sums were written straight to their destination slots
@@ -144,6 +146,7 @@ sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count) {
 void sla_csr_free_dist(sla_csr* A) {
   if (!A->dist) return;
   if (A->ctx && A->ctx->comm_stream) cudaStreamSynchronize(A->ctx->comm_stream);
+  sla_xwin_free(A);                   // in peer-memory mode xfull pointed into the window
   cudaFree(A->dist->xfull);
   delete[] A->dist->seg;
   delete[] A->dist->pseg;
@@ -161,7 +164,7 @@ extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int
   sla_csr_free_dist(A);
   sla_dist_info* d = new (std::nothrow) sla_dist_info();
   if (!d) return sla_fail(c, SLA_ERR_ALLOC, "set_dist alloc");
-  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0; d->pipelined = 0; d->pseg = nullptr;
+  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0; d->pipelined = 0; d->pseg = nullptr; d->xwin = nullptr;
   d->seg = new sla_xseg[nseg > 0 ? nseg : 1];
   for (int s = 0; s < nseg; ++s) {
     if (peer[s] < 0 || peer[s] >= c->world || peer[s] == c->rank || goff[s] < 0 || count[s] < 0 || goff[s] + count[s] > A->n ||
@@ -246,6 +249,7 @@ sla_status sla_dist_exchange_panel(sla_ctx* c, const sla_csr* A, const double* x
 sla_status sla_dist_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local) {
   const sla_dist_info* d = A->dist;
   if (!d || c->world <= 1) return SLA_OK;
+  if (sla_xwin_active(A)) return sla_p2p_exchange_x(c, A, x_local);      // NVLink stores into the peers' buffers (p2p.cu)
   ncclComm_t comm = (ncclComm_t)c->nccl;
   if (d->allgather) {
     SLA_NCCL(c, ncclAllGather(x_local, d->xfull, (size_t)A->m, ncclDouble, comm, c->stream));

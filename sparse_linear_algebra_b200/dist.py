@@ -8,6 +8,7 @@ The planning functions (`row_partition`, `plan_exchange`) are pure Python and ar
 gloo backend (tests/test_dist_cpu.py).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -83,6 +84,41 @@ def exchange_bytes(segs):
     return (8 * sum(c for d, _, _, c in segs if d == 0), 8 * sum(c for d, _, _, c in segs if d == 1))
 
 
+def p2p_wanted():
+    """Peer-memory collectives (csrc/p2p.cu) are on unless SLA_P2P=0; the variable must agree on every rank."""
+    return os.environ.get("SLA_P2P", "1") != "0"
+
+
+def p2p_exchange_wanted():
+    """The peer-memory x exchange is opt-in (SLA_P2P_X=1): measured on B200 (profiles/r01_bench_{p2p,nccl}_n{2,4}.json)
+    it is 3 % faster than ncclAllGather at 2 GPUs but 7 % slower at 4 (dense plan, cfg 2), and ~4 us slower per
+    (#>) than NCCL's grouped send/recv on the Laplacian halos, while the peer-memory all-reduce wins everywhere."""
+    return p2p_wanted() and os.environ.get("SLA_P2P_X", "0") == "1"
+
+
+def _p2p_handshake(export, attach, enable):
+    """Collective set-up of one peer-memory window: every rank exports a 64-byte IPC handle, the handles are
+    gathered in rank order, every rank attaches, and the switch is thrown with the same value everywhere —
+    on only if EVERY rank exported and attached (otherwise the NCCL path keeps running).  Returns the decision."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    buf = C.create_string_buffer(64)
+    st = export(buf) if p2p_wanted() else L.SLA_ERR_INVALID
+    got = [None] * world
+    dist.all_gather_object(got, (int(st), bytes(buf.raw)))
+    ok = all(s == L.SLA_OK for s, _ in got)
+    st2 = L.SLA_ERR_INVALID
+    if ok:
+        blob = C.create_string_buffer(b"".join(h for _, h in got), 64 * world)
+        st2 = attach(blob)
+    sts = [None] * world
+    dist.all_gather_object(sts, int(st2))
+    on = ok and all(s == L.SLA_OK for s in sts)
+    enable(1 if on else 0)
+    return on
+
+
 def init_context(device=None):
     """Create this rank's Context inside an initialised torch.distributed job (any backend).
 
@@ -105,6 +141,9 @@ def init_context(device=None):
     dist.broadcast_object_list(box, src=0)
     ctx = Context(device, rank=rank, world=world, nccl_id=box[0])
     set_default_context(ctx)
+    # the all-reduce behind every dot: peer-memory window over NVLink (falls back to NCCL if any rank cannot map it)
+    ctx.p2p = _p2p_handshake(lambda buf: lib.sla_p2p_export(ctx.h, buf), lambda blob: lib.sla_p2p_attach(ctx.h, blob),
+                             lambda on: ctx.check(lib.sla_p2p_enable(ctx.h, on)))
     return ctx
 
 
@@ -130,6 +169,13 @@ def distribute(ctx, A, starts):
     needs, allgather = densify_needs(starts, needs)
     segs = plan_exchange(rank, starts, needs)
     _install_plan(ctx, A, starts[rank], segs, allgather)
+    # the x exchange: peers store their pieces straight into this rank's window (csrc/p2p.cu)
+    A.dist_p2p = False
+    if getattr(ctx, "p2p", False) and p2p_exchange_wanted():
+        lib = ctx.lib
+        A.dist_p2p = _p2p_handshake(lambda buf: lib.sla_csr_p2p_export(ctx.h, A.h, buf),
+                                    lambda blob: lib.sla_csr_p2p_attach(ctx.h, A.h, blob),
+                                    lambda on: ctx.check(lib.sla_csr_p2p_enable(ctx.h, A.h, on)))
     A.dist_plan = segs
     A.dist_allgather = allgather
     A.row_starts = starts

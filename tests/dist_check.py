@@ -88,7 +88,8 @@ def main():
     dist.all_gather_object(all_fails, fails)
     flat = [f for fl in all_fails for f in fl]
     if rank == 0:
-        print("DIST_CHECK", "OK" if not flat else "FAIL", f"world={world}", flush=True)
+        print("DIST_CHECK", "OK" if not flat else "FAIL", f"world={world}",
+              "collectives=" + ("p2p" if getattr(ctx, "p2p", False) else "nccl"), flush=True)
         for f in flat:
             print("  ", f, flush=True)
     dist.barrier()
