@@ -30,6 +30,10 @@
 #define TRI_LVL_THREADS 256
 #define TRI_SOLVE_THREADS 128
 #define TRI_POLL 4
+#ifndef TRI_MODE
+#define TRI_MODE 0              // solve kernel: 0 = one CTA per 128 positions, 1 = persistent warps (env SLA_TRI_MODE overrides)
+#endif
+#define TRI_LEVELS_IN_FLIGHT 4  // persistent mode: rows in flight = this many levels of average width (env SLA_TRI_LIF)
 #ifndef TRI_BACKOFF_NS
 #define TRI_BACKOFF_NS 0        // nanosleep of a warp that made no progress in a poll round (env SLA_TRI_BACKOFF overrides)
 #endif
@@ -218,6 +222,81 @@ tri_solve_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict_
     if (backoff_ns) {
       if (__any_sync(0xffffffffu, progressed)) sleep_ns = backoff_ns;
       else { __nanosleep(sleep_ns); sleep_ns = min(sleep_ns * 2u, backoff_ns * 16u); }
+    }
+  }
+}
+
+// Persistent variant: a fixed number of warps, each taking 32-position chunks from the ticket until the sweep is
+// done.  The number of rows in flight is chosen by the host from the average level width (a few levels' worth):
+// on a deep, narrow schedule (the 4096^2 stencil: 8191 levels of <= 4096 rows) the non-persistent kernel keeps
+// ~55 levels of rows resident, all polling, and the polls of the 54 levels that cannot run yet saturate the
+// L1 -> L2 request port (ncu: l1tex2xbar 83 % busy, 168 GB of poll traffic) and slow the one level that can.
+// Deadlock-free for any grid size: a position is only waited for by higher positions, and it was claimed
+// (ticket) by a warp that is running.
+template <bool UPPER>
+__global__ void __launch_bounds__(TRI_SOLVE_THREADS)
+tri_solve_persist_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                         const int32_t* __restrict__ diag_idx, const int32_t* __restrict__ order, const double* b,
+                         double* wraw, double* out, int64_t n, unsigned int* ticket, unsigned int backoff_ns) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(ticket, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if ((int64_t)chunk * 32 >= n) break;
+    const int64_t p = (int64_t)chunk * 32 + lane;
+    bool done = p >= n;
+    int row = 0, k = 0, k1 = 0;
+    double acc = 0.0, dv = 1.0, bi = 0.0;
+    if (!done) {
+      row = order[p];
+      const int lo = row_ptr[row], hi = row_ptr[row + 1], d = diag_idx[row];
+      dv = val[d];
+      bi = b[row];
+      k = UPPER ? d + 1 : lo;
+      k1 = UPPER ? hi : d;
+    }
+    unsigned int sleep_ns = backoff_ns;
+    while (__any_sync(0xffffffffu, !done)) {
+      bool progressed = false;
+      if (!done) {
+        if (k < k1) {
+          unsigned long long bits[TRI_POLL];
+          double a[TRI_POLL];
+#pragma unroll
+          for (int q = 0; q < TRI_POLL; ++q) {
+            bits[q] = TRI_SENTINEL;
+            a[q] = 0.0;
+            if (k + q < k1) {
+              a[q] = val[k + q];
+              bits[q] = ld_relaxed_u64(wraw + col[k + q]);
+            }
+          }
+          bool go = true;
+#pragma unroll
+          for (int q = 0; q < TRI_POLL; ++q) {
+            go = go && bits[q] != TRI_SENTINEL;
+            if (go) {                    // ascending j, strict left fold from 0   Sparse.hs:762, 795
+              acc = __dadd_rn(acc, __dmul_rn(a[q], __longlong_as_double((long long)bits[q])));
+              ++k;
+              progressed = true;
+            }
+          }
+        }
+        if (k >= k1) {
+          const double w = __ddiv_rn(__dsub_rn(bi, acc), dv);      // wi = (bi - r) / lii   Sparse.hs:761, 794
+          unsigned long long wb = (unsigned long long)__double_as_longlong(w);
+          if (wb == TRI_SENTINEL) wb = TRI_CANONICAL_NAN;
+          st_relaxed_u64(wraw + row, wb);
+          out[row] = near_zero(w) ? 0.0 : w;                       // sparsifySV   Sparse.hs:777, 811
+          done = true;
+          progressed = true;
+        }
+      }
+      if (backoff_ns) {
+        if (__any_sync(0xffffffffu, progressed)) sleep_ns = backoff_ns;
+        else { __nanosleep(sleep_ns); sleep_ns = min(sleep_ns * 2u, backoff_ns * 16u); }
+      }
     }
   }
 }
@@ -478,7 +557,24 @@ sla_status tri_solve(sla_ctx* c, const sla_csr* A_, const sla_vec* b, sla_vec* x
   const unsigned grid = (unsigned)((n + TRI_SOLVE_THREADS - 1) / TRI_SOLVE_THREADS);
   unsigned int backoff = TRI_BACKOFF_NS;
   if (const char* e = getenv("SLA_TRI_BACKOFF")) backoff = (unsigned int)atoi(e);
-  if (upper)
+  int mode = TRI_MODE;                   // 0: one CTA per 128 positions; 1: persistent warps sized from the level width
+  if (const char* e = getenv("SLA_TRI_MODE")) mode = atoi(e);
+  if (mode == 1) {
+    // rows in flight ~ TRI_LEVELS_IN_FLIGHT levels of average width, at least one CTA per SM, at most full residency
+    int lif = TRI_LEVELS_IN_FLIGHT;
+    if (const char* e = getenv("SLA_TRI_LIF")) lif = atoi(e);
+    const int64_t width = (n + P->nlevels - 1) / (P->nlevels > 0 ? P->nlevels : 1);
+    int64_t ctas = (width * lif + TRI_SOLVE_THREADS - 1) / TRI_SOLVE_THREADS;
+    if (ctas < SLA_NUM_SMS) ctas = SLA_NUM_SMS;
+    if (ctas > SLA_NUM_SMS * 12) ctas = SLA_NUM_SMS * 12;
+    if (ctas > grid) ctas = grid;
+    if (upper)
+      tri_solve_persist_kernel<true><<<(unsigned)ctas, TRI_SOLVE_THREADS, 0, c->stream>>>(A->row_ptr, A->col, A->val, A->tri_diag, P->order,
+                                                                                         b->d, A->tri_w, x->d, n, A->tri_ticket, backoff);
+    else
+      tri_solve_persist_kernel<false><<<(unsigned)ctas, TRI_SOLVE_THREADS, 0, c->stream>>>(A->row_ptr, A->col, A->val, A->tri_diag, P->order,
+                                                                                          b->d, A->tri_w, x->d, n, A->tri_ticket, backoff);
+  } else if (upper)
     tri_solve_kernel<true><<<grid, TRI_SOLVE_THREADS, 0, c->stream>>>(A->row_ptr, A->col, A->val, A->tri_diag, P->order, b->d, A->tri_w,
                                                                       x->d, n, A->tri_ticket, backoff);
   else
