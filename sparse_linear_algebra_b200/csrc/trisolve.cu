@@ -12,7 +12,9 @@
 //     Dependencies inside the CTA's own chunk (the i-1 neighbour of a stencil) are polled in shared memory.
 //     Rows are then sorted by (level, row) with a stable radix sort.
 //   solve (two launches: sentinel fill, sweep)
-//     thread p owns row order[p]; CTAs take 128-position chunks from a ticket, again in dependency order.  The
+//     thread p owns row order[p]; a fixed set of persistent warps takes 32-position chunks from a ticket, again in
+//     dependency order; the number of rows in flight is ~4 levels of average width (measured on the 4096^2 stencil:
+//     7.8 ms against 22.5 ms for one CTA per 128 positions, profiles/r01_sptrsv_sweep.txt).  The
 //     partial solution itself is the ready flag: w starts as a NaN pattern no arithmetic produces, a consumer polls
 //     w_j with ld.relaxed.gpu until it changes.  Up to four dependencies are polled per round so that a row whose
 //     dependencies are ready costs one L2 round trip, and they are consumed strictly in ascending column order
@@ -31,7 +33,7 @@
 #define TRI_SOLVE_THREADS 128
 #define TRI_POLL 4
 #ifndef TRI_MODE
-#define TRI_MODE 0              // solve kernel: 0 = one CTA per 128 positions, 1 = persistent warps (env SLA_TRI_MODE overrides)
+#define TRI_MODE 1              // solve kernel: 0 = one CTA per 128 positions, 1 = persistent warps (env SLA_TRI_MODE overrides)
 #endif
 #define TRI_LEVELS_IN_FLIGHT 4  // persistent mode: rows in flight = this many levels of average width (env SLA_TRI_LIF)
 #ifndef TRI_BACKOFF_NS
