@@ -11,11 +11,12 @@
 -- (BICGSTAB a holds SpVector a, Sparse.hs:962-963), so the drop-in is this module exporting the same names
 -- over opaque device handles plus `toDevice` / `fromDevice` marshalling, not a new class instance.
 module Numeric.LinearAlgebra.Sparse.B200
-  ( Ctx, DMatrix, DVector, BICGSTAB(..), CGS(..)
+  ( Ctx, DMatrix, DVector, BICGSTAB(..), CGS(..), CGNE(..)
   , withB200, toDeviceSM, toDeviceSV, fromDeviceSV
   , (#>), (<#), (<.>), (^+^), (^-^), (.*), (./), norm2, normalize2, transpose
-  , bicgsInit, bicgstabStep, cgsInit, cgsStep
+  , bicgsInit, bicgstabStep, cgsInit, cgsStep, cgneInit, cgneStep
   , LinSolveMethod(..), linSolve0, arnoldi, (<\>)
+  , diagPartitions, jacobiPre, mSsorPre, triLowerSolve, triUpperSolve
   ) where
 
 import Control.Exception (bracket, throwIO)
@@ -27,7 +28,7 @@ import Foreign.C.String (CString, peekCString)
 import Foreign.C.Types
 
 -- the reference's own types, used only for marshalling and for the exceptions we re-throw
-import Control.Exception.Common (OperandSizeMismatch(..), IterationException(..))
+import Control.Exception.Common (OperandSizeMismatch(..), IterationException(..), MatrixException(..))
 import Data.Sparse.SpMatrix (SpMatrix, immSM, nrows, ncols)
 import Data.Sparse.SpVector (SpVector, fromListDenseSV, toDenseListSV, dim)
 import qualified Data.Sparse.Internal.IntM as I
@@ -63,6 +64,13 @@ foreign import ccall safe "sla_bicgstab_init"   c_bicg_init   :: Ptr SlaCtx -> P
 foreign import ccall safe "sla_bicgstab_step"   c_bicg_step   :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaKrylov -> IO Status
 foreign import ccall safe "sla_cgs_init"        c_cgs_init    :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaVec -> Ptr (Ptr SlaKrylov) -> IO Status
 foreign import ccall safe "sla_cgs_step"        c_cgs_step    :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaKrylov -> IO Status
+foreign import ccall safe "sla_cgne_init"       c_cgne_init   :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaVec -> Ptr (Ptr SlaKrylov) -> IO Status
+foreign import ccall safe "sla_cgne_step"       c_cgne_step   :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaKrylov -> IO Status
+foreign import ccall safe "sla_csr_diag_partitions" c_diag_parts :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr (Ptr SlaCsr) -> Ptr (Ptr SlaCsr) -> Ptr (Ptr SlaCsr) -> IO Status
+foreign import ccall safe "sla_jacobi_pre"      c_jacobi_pre  :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr (Ptr SlaCsr) -> IO Status
+foreign import ccall safe "sla_mssor_pre"       c_mssor_pre   :: Ptr SlaCtx -> Ptr SlaCsr -> Double -> Ptr (Ptr SlaCsr) -> Ptr (Ptr SlaCsr) -> IO Status
+foreign import ccall safe "sla_tri_lower_solve" c_tri_lower   :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaVec -> IO Status
+foreign import ccall safe "sla_tri_upper_solve" c_tri_upper   :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaVec -> IO Status
 foreign import ccall safe "sla_krylov_view"     c_kry_view    :: Ptr SlaCtx -> Ptr SlaKrylov -> CInt -> Ptr (Ptr SlaVec) -> IO Status
 foreign import ccall safe "&sla_krylov_free"    p_kry_free    :: FunPtr (Ptr SlaKrylov -> IO ())
 foreign import ccall safe "sla_linsolve0"       c_linsolve0   :: Ptr SlaCtx -> CInt -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaVec -> Ptr () -> Ptr SlaVec -> Ptr CInt -> Ptr Double -> IO Status
@@ -77,6 +85,7 @@ check (Ctx c) who st = when (st /= 0) $ do
     1 -> throwIO (MatVecSizeMismatchException who (0, 0) 0)             -- SLA_ERR_SIZE_MISMATCH
     2 -> ioError (userError "insertSpMatrix : index out of bounds")     -- SLA_ERR_OOB_INDEX  (SpMatrix.hs:205-208)
     3 -> throwIO (IterE who msg :: IterationException ())               -- SLA_ERR_UNSUPPORTED_METHOD
+    10 -> throwIO (NeedsPivoting who msg :: MatrixException Double)     -- SLA_ERR_NEEDS_PIVOTING (Sparse.hs:757, 791)
     _ -> ioError (userError (who ++ ": " ++ msg))
 
 withB200 :: Int -> (Ctx -> IO a) -> IO a
@@ -192,6 +201,41 @@ bicgstabStep (DMatrix ctx@(Ctx c) fa) (DVector _ fr) st@(BICGSTAB fs) =
 cgsStep :: DMatrix -> DVector -> CGS -> IO CGS                                  -- Sparse.hs:928-939
 cgsStep (DMatrix ctx@(Ctx c) fa) (DVector _ fr) st@(CGS fs) =
   withForeignPtr fa $ \pa -> withForeignPtr fr $ \pr -> withForeignPtr fs $ \ps -> c_cgs_step c pa pr ps >>= check ctx "cgsStep" >> return st
+
+newtype CGNE = CGNE (ForeignPtr SlaKrylov)
+cgneInit :: DMatrix -> DVector -> DVector -> IO CGNE                            -- Sparse.hs:862-866
+cgneInit aa b x0 = CGNE <$> initWith "cgneInit" c_cgne_init aa b x0
+cgneStep :: DMatrix -> CGNE -> IO CGNE                                          -- Sparse.hs:868-878 (A^T is cached on the device)
+cgneStep (DMatrix ctx@(Ctx c) fa) st@(CGNE fs) =
+  withForeignPtr fa $ \pa -> withForeignPtr fs $ \ps -> c_cgne_step c pa ps >>= check ctx "cgneStep" >> return st
+
+-- | Preconditioners and triangular solves (Sparse.hs:673-721, 750-811).  The reference does not export the
+--   preconditioners (Sparse.hs:17); the names are kept for the day it does.
+wrapM :: Ctx -> Ptr (Ptr SlaCsr) -> IO DMatrix
+wrapM ctx pp = peek pp >>= fmap (DMatrix ctx) . newForeignPtr p_csr_free
+
+diagPartitions :: DMatrix -> IO (DMatrix, DMatrix, DMatrix)                    -- (sub-diagonal, diagonal, super-diagonal)
+diagPartitions (DMatrix ctx@(Ctx c) fa) = withForeignPtr fa $ \pa -> alloca $ \pe -> alloca $ \pd -> alloca $ \pf -> do
+  c_diag_parts c pa pe pd pf >>= check ctx "diagPartitions"
+  (,,) <$> wrapM ctx pe <*> wrapM ctx pd <*> wrapM ctx pf
+
+jacobiPre :: DMatrix -> IO DMatrix                                             -- recip <$> extractDiag x
+jacobiPre (DMatrix ctx@(Ctx c) fa) = withForeignPtr fa $ \pa -> alloca $ \pm -> c_jacobi_pre c pa pm >>= check ctx "jacobiPre" >> wrapM ctx pm
+
+mSsorPre :: DMatrix -> Double -> IO (DMatrix, DMatrix)                         -- (l, r), Sparse.hs:713-721
+mSsorPre (DMatrix ctx@(Ctx c) fa) omega = withForeignPtr fa $ \pa -> alloca $ \pl -> alloca $ \pr -> do
+  c_mssor_pre c pa omega pl pr >>= check ctx "mSsorPre"
+  (,) <$> wrapM ctx pl <*> wrapM ctx pr
+
+triSolveWith :: String -> (Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaVec -> IO Status) -> DMatrix -> DVector -> IO DVector
+triSolveWith who f (DMatrix ctx@(Ctx c) fa) b@(DVector _ fb) = do
+  w@(DVector _ fw) <- dimD b >>= newVec ctx
+  withForeignPtr fa $ \pa -> withForeignPtr fb $ \pb -> withForeignPtr fw $ \pw -> f c pa pb pw >>= check ctx who
+  return w
+
+triLowerSolve, triUpperSolve :: DMatrix -> DVector -> IO DVector              -- Sparse.hs:750-778, 784-811 (NeedsPivoting on a nearZero diagonal)
+triLowerSolve = triSolveWith "triLowerSolve" c_tri_lower
+triUpperSolve = triSolveWith "triUpperSolve" c_tri_upper
 
 data LinSolveMethod = GMRES_ | CGNE_ | BCG_ | CGS_ | BICGSTAB_ deriving (Eq, Show, Enum)   -- Sparse.hs:1007-1012
 
