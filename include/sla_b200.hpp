@@ -38,6 +38,7 @@ struct Error : std::runtime_error {
 struct MatVecSizeMismatchException : Error { using Error::Error; };   // OperandSizeMismatch
 struct OutOfBoundsIndexError : Error { using Error::Error; };         // error "insertSpMatrix : index out of bounds"
 struct IterE : Error { using Error::Error; };                         // IterationException IterE
+struct NeedsPivoting : Error { using Error::Error; };                 // MatrixException NeedsPivoting (triangular solves)
 
 enum LinSolveMethod { GMRES_ = SLA_GMRES_, CGNE_ = SLA_CGNE_, BCG_ = SLA_BCG_, CGS_ = SLA_CGS_, BICGSTAB_ = SLA_BICGSTAB_ };
 
@@ -57,6 +58,7 @@ class Context {
       case SLA_ERR_SIZE_MISMATCH: throw MatVecSizeMismatchException(s, msg);
       case SLA_ERR_OOB_INDEX: throw OutOfBoundsIndexError(s, msg);
       case SLA_ERR_UNSUPPORTED_METHOD: throw IterE(s, msg);
+      case SLA_ERR_NEEDS_PIVOTING: throw NeedsPivoting(s, msg);
       default: throw Error(s, msg);
     }
   }
@@ -179,6 +181,8 @@ class SpMatrix {
   }
   sla_csr* get() const { return a_.get(); }
   const Context& ctx() const { return c_; }
+  // takes ownership of a handle the C ABI returned (preconditioners, partitions)
+  static SpMatrix adopt(const Context& c, sla_csr* a) { return SpMatrix(c, a); }
 
  private:
   SpMatrix(const Context& c, sla_csr* a) : c_(c) { a_.reset(a, [](sla_csr* p) { sla_csr_free(p); }); }
@@ -223,6 +227,44 @@ inline KrylovState cgsInit(const SpMatrix& aa, const SpVector& b, const SpVector
 inline KrylovState& cgsStep(const SpMatrix& aa, const SpVector& rhat, KrylovState& st) {
   aa.ctx().check(sla_cgs_step(aa.ctx().get(), aa.get(), rhat.get(), st.get()));
   return st;
+}
+
+inline KrylovState cgneInit(const SpMatrix& aa, const SpVector& b, const SpVector& x0) {      // Sparse.hs:862-866
+  sla_krylov* st = nullptr;
+  aa.ctx().check(sla_cgne_init(aa.ctx().get(), aa.get(), b.get(), x0.get(), &st));
+  return KrylovState(aa.ctx(), st);
+}
+inline KrylovState& cgneStep(const SpMatrix& aa, KrylovState& st) {                            // Sparse.hs:868-878
+  aa.ctx().check(sla_cgne_step(aa.ctx().get(), aa.get(), st.get()));
+  return st;
+}
+
+// ---- preconditioners and triangular solves (Sparse.hs:673-721, 750-811)
+struct DiagPartitions { SpMatrix e, d, f; };     // strictly sub-diagonal, diagonal, strictly super-diagonal
+inline DiagPartitions diagPartitions(const SpMatrix& aa) {
+  sla_csr *e = nullptr, *d = nullptr, *f = nullptr;
+  aa.ctx().check(sla_csr_diag_partitions(aa.ctx().get(), aa.get(), &e, &d, &f));
+  return DiagPartitions{SpMatrix::adopt(aa.ctx(), e), SpMatrix::adopt(aa.ctx(), d), SpMatrix::adopt(aa.ctx(), f)};
+}
+inline SpMatrix jacobiPre(const SpMatrix& aa) {                       // recip <$> extractDiag x
+  sla_csr* m = nullptr;
+  aa.ctx().check(sla_jacobi_pre(aa.ctx().get(), aa.get(), &m));
+  return SpMatrix::adopt(aa.ctx(), m);
+}
+inline std::pair<SpMatrix, SpMatrix> mSsorPre(const SpMatrix& aa, double omega) {   // (l, r)
+  sla_csr *l = nullptr, *r = nullptr;
+  aa.ctx().check(sla_mssor_pre(aa.ctx().get(), aa.get(), omega, &l, &r));
+  return {SpMatrix::adopt(aa.ctx(), l), SpMatrix::adopt(aa.ctx(), r)};
+}
+inline SpVector triLowerSolve(const SpMatrix& ll, const SpVector& b) {    // forward substitution; NeedsPivoting on a nearZero diagonal
+  SpVector w(ll.ctx(), b.dim());
+  ll.ctx().check(sla_tri_lower_solve(ll.ctx().get(), ll.get(), b.get(), w.get()));
+  return w;
+}
+inline SpVector triUpperSolve(const SpMatrix& uu, const SpVector& w) {    // backward substitution
+  SpVector x(uu.ctx(), w.dim());
+  uu.ctx().check(sla_tri_upper_solve(uu.ctx().get(), uu.get(), w.get(), x.get()));
+  return x;
 }
 
 struct SolveInfo { int iters = 0; double resnorm = 0; };
