@@ -243,8 +243,9 @@ def run_gpu(args):
     extra = {"x_exchange_recv_bytes_per_rank": recv_bytes}
     if world > 1:
         extra["collectives"] = {"allreduce": "peer-memory kernel over NVLink (csrc/p2p.cu)" if getattr(ctx, "p2p", False) else "nccl",
-                                "x_exchange": "peer-memory push kernel (csrc/p2p.cu)" if getattr(A, "dist_p2p", False)
-                                else ("ncclAllGather" if getattr(A, "dist_allgather", False) else "nccl send/recv")}
+                                "x_exchange": {1: "peer-memory push kernel (csrc/p2p.cu)",
+                                               2: "copy-engine all-gather consumed in arrival order (csrc/p2p.cu mode 2)"}.get(
+                                    getattr(A, "dist_p2p_mode", 0), "ncclAllGather" if getattr(A, "dist_allgather", False) else "nccl send/recv")}
 
     def sptrsv_extra(tag, M, rhs):
         if args.no_sptrsv:

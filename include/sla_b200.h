@@ -102,7 +102,8 @@ sla_status sla_p2p_enable(sla_ctx*, int on);
 int        sla_p2p_enabled(const sla_ctx*);
 sla_status sla_csr_p2p_export(sla_ctx*, sla_csr*, void* handle64);
 sla_status sla_csr_p2p_attach(sla_ctx*, sla_csr*, const void* handles /* world x 64 bytes */);
-sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on);
+sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on /* 0 off, 1 push kernel, 2 copy engines + arrival-order panels */);
+int        sla_csr_p2p_mode(const sla_csr*);      /* the mode in force (2 falls back to 1 when the plan is not dense / equal-block) */
 sla_status sla_vec_generate_slice(sla_ctx*, int64_t i0, int64_t n, uint64_t seed, sla_vec** out);
 sla_status sla_csr_dims(const sla_csr*, int64_t* m, int64_t* n, int64_t* nnz);
 sla_status sla_csr_to_host(sla_ctx*, const sla_csr*, int32_t* row_ptr, int32_t* col_idx, double* val);

@@ -291,6 +291,9 @@ sla_status sla_p2p_allreduce(sla_ctx* c, int nv, int src, int fin, int dst);
 sla_status sla_p2p_check(sla_ctx* c);
 void sla_p2p_free(sla_ctx* c);
 bool sla_xwin_active(const sla_csr* A);
+int sla_xwin_mode(const sla_csr* A);                                                             // 0 off, 1 push kernel, 2 arrival order
+sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_local);
+sla_status sla_p2p_arrival_wait(sla_ctx* c, const sla_csr* A, int src);
 sla_status sla_p2p_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local);
 void sla_xwin_free(sla_csr* A);
 void sla_csr_free_bsr(sla_csr* A);

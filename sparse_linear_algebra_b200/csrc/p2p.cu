@@ -17,6 +17,13 @@
 // Every wait has a cycle-count timeout that raises a device error flag (reported as SLA_ERR_COMM at the next
 // synchronisation) instead of hanging the GPU.
 //
+// Mode 2 of the x exchange (SLA_P2P_X=2; WRITTEN BUT NOT YET RUN ON HARDWARE — round-2 experiment): for dense plans
+// with equal blocks the blocks travel on the COPY ENGINES in a staggered order (rank r sends to r+1, r+2, ... on the
+// comm stream, one flag per destination after each copy) and the (#>) runs one column panel per source rank in ARRIVAL
+// order (own block, then r-1, r-2, ...), each panel kernel preceded by a one-warp wait on that source's flag — so the
+// transfer of block k+1 hides behind the kernel of panel k.  Row sums are then folded in rotated column order:
+// within the fp64 bound of SURVEY.md §8(d), no longer bit-identical to the single-GPU result.
+//
 // Enabling is a COLLECTIVE decision taken by the host (every rank exported and attached successfully and
 // SLA_P2P != 0); otherwise the NCCL path of dist.cu runs unchanged.
 #include "common.cuh"
@@ -43,6 +50,7 @@ struct sla_p2p {                                 // per context: the all-reduce 
 
 struct sla_xwin {                                // per distributed matrix: [256 B flags][x buffer 0][x buffer 1]
   int enabled;
+  int mode;                                      // 1: push kernel + wait for every peer; 2: copy engines, arrival-order panels
   char* win;
   size_t buf_bytes;
   char* peer[SLA_MAX_WORLD];
@@ -143,6 +151,17 @@ p2p_push_kernel(const p2p_item* __restrict__ items, int nitems, char* const* __r
   const int t = threadIdx.x;
   if (t < world && t != rank) st_release_sys_u64(reinterpret_cast<unsigned long long*>(peer[t]) + rank, seq);
   if (t < world && t != rank) wait_flag(reinterpret_cast<const unsigned long long*>(peer[rank]) + t, seq, err);
+}
+
+// mode 2: the flag that follows a copy-engine block on the comm stream, and the per-source wait before a panel kernel
+__global__ void p2p_flag_kernel(unsigned long long* dst, unsigned long long seq) {
+  __threadfence_system();
+  st_release_sys_u64(dst, seq);
+}
+__global__ void __launch_bounds__(32)
+p2p_wait_kernel(const unsigned long long* flags, unsigned int mask, unsigned long long seq, int* err) {
+  const int t = threadIdx.x;
+  if (t < SLA_MAX_WORLD && ((mask >> t) & 1u)) wait_flag(flags + t, seq, err);
 }
 
 sla_status open_peers(sla_ctx* c, const void* handles, char* own, char** peer) {
@@ -316,7 +335,20 @@ extern "C" sla_status sla_csr_p2p_enable(sla_ctx* c, sla_csr* A, int on) {
   if (!d->xwin) return on ? sla_fail(c, SLA_ERR_INVALID, "p2p: no matrix window exported") : SLA_OK;
   if (on && !d->xwin->peer[c->rank]) return sla_fail(c, SLA_ERR_INVALID, "p2p: matrix windows not attached");
   if (on && !sla_p2p_active(c)) return sla_fail(c, SLA_ERR_INVALID, "p2p: the context-level switch is off");
+  int mode = on ? 1 : 0;
+  if (on == 2) {
+    // arrival-order mode needs one column panel per source rank: equal blocks in rank order, panel width = block size.
+    // The test only looks at global quantities, so every rank takes the same branch.
+    const int W = c->world;
+    const bool eligible = A->n % W == 0 && A->m == A->n / W && d->row0 == (int64_t)c->rank * A->m && A->m % 16 == 0 && A->m > 0 &&
+                          W <= SLA_MAX_PANELS && c->comm_stream != nullptr;
+    if (eligible) {
+      SLA_TRY(sla_csr_force_panels(c, A, W));
+      if (A->npanels == W && A->panel_width == A->m) mode = 2;
+    }
+  }
   d->xwin->enabled = on ? 1 : 0;
+  d->xwin->mode = mode;
   if (on) {
     // the kernels now read the remote entries from the window: the private gathered-x buffer is not needed
     SLA_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -328,6 +360,37 @@ extern "C" sla_status sla_csr_p2p_enable(sla_ctx* c, sla_csr* A, int on) {
 }
 
 bool sla_xwin_active(const sla_csr* A) { return A->dist && A->dist->xwin && A->dist->xwin->enabled; }
+int sla_xwin_mode(const sla_csr* A) { return sla_xwin_active(A) ? A->dist->xwin->mode : 0; }
+extern "C" int sla_csr_p2p_mode(const sla_csr* A) { return A ? sla_xwin_mode(A) : 0; }
+
+// mode 2, step 1: once x is final, the local block goes to the peers on the copy engines (comm stream) in the order
+// r+1, r+2, ..., each copy followed by this rank's flag on that peer; flips the double buffer.
+sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_local) {
+  sla_dist_info* d = A->dist;
+  sla_xwin* X = d->xwin;
+  const int W = c->world;
+  X->seq++;
+  const size_t off = P2P_FLAG_BYTES + (size_t)(X->seq & 1ull) * X->buf_bytes;
+  SLA_CUDA(c, cudaEventRecord(c->ev_x0, c->stream));                   // x is final; my earlier panel kernels are done
+  SLA_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_x0, 0));
+  for (int k = 1; k < W; ++k) {
+    const int q = (c->rank + k) % W;
+    double* dst = reinterpret_cast<double*>(X->peer[q] + off) + d->row0;
+    SLA_CUDA(c, cudaMemcpyAsync(dst, x_local, sizeof(double) * (size_t)A->m, cudaMemcpyDefault, c->comm_stream));
+    p2p_flag_kernel<<<1, 1, 0, c->comm_stream>>>(reinterpret_cast<unsigned long long*>(X->peer[q]) + c->rank, X->seq);
+    SLA_LAUNCH_CHECK(c);
+  }
+  d->xfull = reinterpret_cast<double*>(X->win + off);
+  return SLA_OK;
+}
+
+// mode 2, step 2 (compute stream): block of rank `src` has arrived in the current buffer
+sla_status sla_p2p_arrival_wait(sla_ctx* c, const sla_csr* A, int src) {
+  sla_xwin* X = A->dist->xwin;
+  p2p_wait_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const unsigned long long*>(X->win), 1u << src, X->seq, c->p2p->d_err);
+  SLA_LAUNCH_CHECK(c);
+  return SLA_OK;
+}
 
 // pushes the planned pieces of x_local to the peers and waits for theirs; afterwards A->dist->xfull is the buffer
 // the next kernel reads
@@ -352,6 +415,7 @@ void sla_xwin_free(sla_csr* A) {
   sla_xwin* X = d->xwin;
   sla_ctx* c = A->ctx;
   if (c) cudaStreamSynchronize(c->stream);
+  if (c && c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c) close_peers(c, X->peer);
   cudaFree(X->d_peer); cudaFree(X->d_items); cudaFree(X->d_ticket);
   if (X->enabled) d->xfull = nullptr;            // it pointed into the window

@@ -690,6 +690,36 @@ static sla_status launch_any(sla_ctx* c, int epi, bool acc, bool dist, const Spm
   return acc ? launch_epi<true, false>(c, epi, a) : launch_epi<false, false>(c, epi, a);
 }
 
+// Row-partitioned (#>) in ARRIVAL order (p2p.cu mode 2, SLA_P2P_X=2; not yet run on hardware): one column panel per
+// source rank; the own block first, then the blocks in the order the staggered copy-engine all-gather delivers them,
+// each panel kernel preceded by a one-warp wait for that source's flag.  The fold over a row's entries is in rotated
+// column order: a valid summation of the same products (SURVEY.md §8(d) bound), not the bit-exact ascending fold.
+static sla_status spmv_launch_arrival(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi, const double* u0, int fin, int dst) {
+  const int W = c->world;
+  SLA_TRY(sla_p2p_arrival_begin(c, A, x));
+  SpmvArgs a;
+  a.hints = A->hints; a.x = x; a.u0 = u0; a.fin = fin; a.dst = dst;
+  a.xr = A->dist->xfull; a.col0 = (int)A->dist->row0; a.ncl = (int)A->m; a.tile0 = 0;
+  double* ybuf = y;
+  if (epi == EPI_RESNORM) {
+    if (!c->scratch_r || c->scratch_r->n != A->m) {
+      sla_vec_free(c->scratch_r); c->scratch_r = nullptr;
+      SLA_TRY(sla_vec_alloc(c, A->m, &c->scratch_r));
+    }
+    ybuf = c->scratch_r->d;
+  }
+  for (int k = 0; k < W; ++k) {
+    const int q = (c->rank - k + W) % W;                 // rank r-1 sends to me first, r-2 second, ...
+    if (k > 0) SLA_TRY(sla_p2p_arrival_wait(c, A, q));
+    const sla_panel& pn = A->panels[q];
+    a.row_ptr = pn.row_ptr; a.col = pn.col; a.val = pn.val; a.tile_row = pn.tile_row;
+    a.ntiles = pn.ntiles; a.skew_a = pn.skew_a;
+    a.yin = k == 0 ? nullptr : ybuf; a.y = ybuf;
+    SLA_TRY(launch_any(c, k + 1 == W ? epi : EPI_NONE, k > 0, true, a));
+  }
+  return SLA_OK;
+}
+
 // y = A x with an optional fused epilogue.  u1 is reserved (EPI_DOT2_YY uses y itself).
 // For a row block of a distributed matrix, x is the LOCAL slice; the remote entries are exchanged first.
 sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi,
@@ -697,6 +727,8 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   (void)u1;
   if (A->ntiles > SLA_MAX_PARTIALS) return sla_fail(c, SLA_ERR_INVALID, "spmv: matrix has too many tiles");
   const bool dist = A->dist != nullptr;
+  if (dist && c->world > 1 && sla_xwin_mode(A) == 2 && A->npanels == c->world && A->m > 0)
+    return spmv_launch_arrival(c, A, x, y, epi, u0, fin, dst);
   // Dense multi-GPU plans are pipelined: the exchange of panel p+1 (comm stream) overlaps the kernel of panel p.
   const bool pipelined = dist && A->dist->pipelined && A->npanels >= 2 && c->world > 1;
   if (pipelined) {

@@ -89,11 +89,18 @@ def p2p_wanted():
     return os.environ.get("SLA_P2P", "1") != "0"
 
 
-def p2p_exchange_wanted():
-    """The peer-memory x exchange is opt-in (SLA_P2P_X=1): measured on B200 (profiles/r01_bench_{p2p,nccl}_n{2,4}.json)
-    it is 3 % faster than ncclAllGather at 2 GPUs but 7 % slower at 4 (dense plan, cfg 2), and ~4 us slower per
-    (#>) than NCCL's grouped send/recv on the Laplacian halos, while the peer-memory all-reduce wins everywhere."""
-    return p2p_wanted() and os.environ.get("SLA_P2P_X", "0") == "1"
+def p2p_exchange_mode():
+    """Transport of the x exchange (SLA_P2P_X): 0 = NCCL (default), 1 = peer-memory push kernel, 2 = copy-engine
+    all-gather consumed in arrival order (dense equal-block plans; falls back to 1 otherwise; not yet run on hardware).
+    Measured on B200 (profiles/r01_bench_{p2p,nccl}_n{2,4}.json): the push kernel is 3 % faster than ncclAllGather at
+    2 GPUs but 7 % slower at 4 (cfg 2), and ~4 us slower per (#>) than NCCL's grouped send/recv on the Laplacian halos,
+    while the peer-memory all-reduce wins everywhere — hence NCCL stays the default for the exchange."""
+    if not p2p_wanted():
+        return 0
+    try:
+        return max(0, min(2, int(os.environ.get("SLA_P2P_X", "0"))))
+    except ValueError:
+        return 0
 
 
 def _p2p_handshake(export, attach, enable):
@@ -171,11 +178,14 @@ def distribute(ctx, A, starts):
     _install_plan(ctx, A, starts[rank], segs, allgather)
     # the x exchange: peers store their pieces straight into this rank's window (csrc/p2p.cu)
     A.dist_p2p = False
-    if getattr(ctx, "p2p", False) and p2p_exchange_wanted():
+    A.dist_p2p_mode = 0
+    mode = p2p_exchange_mode()
+    if getattr(ctx, "p2p", False) and mode:
         lib = ctx.lib
         A.dist_p2p = _p2p_handshake(lambda buf: lib.sla_csr_p2p_export(ctx.h, A.h, buf),
                                     lambda blob: lib.sla_csr_p2p_attach(ctx.h, A.h, blob),
-                                    lambda on: ctx.check(lib.sla_csr_p2p_enable(ctx.h, A.h, on)))
+                                    lambda on: ctx.check(lib.sla_csr_p2p_enable(ctx.h, A.h, mode if on else 0)))
+        A.dist_p2p_mode = lib.sla_csr_p2p_mode(A.h)
     A.dist_plan = segs
     A.dist_allgather = allgather
     A.row_starts = starts

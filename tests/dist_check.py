@@ -50,7 +50,16 @@ def main():
         xo = ora.SpVector.synth(seed + 1, n)
         y = (A @ x).toDenseListSV()
         yo = Ao.matVec(xo).toDenseListSV()
-        check(f"{name}: row-partitioned (#>) bit-exact", y.tobytes() == yo[r0:r1].tobytes())
+        if getattr(A, "dist_p2p_mode", 0) == 2:
+            # arrival-order panels fold each row in rotated column order: a valid summation of the same products,
+            # |dy_i| <= (k_i + 2) u sum_j |a_ij x_j|  (SURVEY.md section 8(d)), no longer the bit-exact ascending fold
+            rp, cj, vv = Ao.toCSR()
+            xa = np.abs(xo.toDenseListSV())
+            mag = np.add.reduceat(np.abs(vv) * xa[cj], rp[:-1]) if len(vv) else np.zeros(n)
+            bound = (np.diff(rp) + 2) * 2.0 ** -53 * mag
+            check(f"{name}: row-partitioned (#>) within the fp64 bound (arrival order)", bool(np.all(np.abs(y - yo[r0:r1]) <= bound[r0:r1])))
+        else:
+            check(f"{name}: row-partitioned (#>) bit-exact", y.tobytes() == yo[r0:r1].tobytes())
         # <.> and norm2 across ranks
         d, do = x.dot(A @ x), xo.dot(Ao.matVec(xo))
         check(f"{name}: distributed <.>", abs(d - do) <= 1e-12 * abs(do) + 1e-300)
@@ -89,7 +98,7 @@ def main():
     flat = [f for fl in all_fails for f in fl]
     if rank == 0:
         print("DIST_CHECK", "OK" if not flat else "FAIL", f"world={world}",
-              "collectives=" + ("p2p" if getattr(ctx, "p2p", False) else "nccl"), flush=True)
+              "collectives=" + ("p2p" if getattr(ctx, "p2p", False) else "nccl"), "x_exchange_mode=" + os.environ.get("SLA_P2P_X", "0"), flush=True)
         for f in flat:
             print("  ", f, flush=True)
     dist.barrier()
