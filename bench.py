@@ -38,12 +38,17 @@ def load_peak():
 
 
 def load_traffic():
-    """DRAM bytes per SpMV launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    """DRAM bytes of the cfg-2 (#>) from the committed ncu --set full capture (profiles/traffic.json): the step is TWO
+    launches of spmv_tile_kernel (one per column panel), so the per-step figure — the one comparable with
+    `algorithmic_bytes_per_step` — is the sum over both.  Returns (per_step, per_launch, launches) or Nones."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("spmv_cfg2_dram_bytes_per_launch")
+            d = json.load(f)
+        per_launch = d.get("spmv_cfg2_dram_bytes_per_launch")
+        launches = d.get("spmv_cfg2_launches_per_step", 2)
+        return d.get("spmv_cfg2_dram_bytes_per_step", per_launch * launches if per_launch else None), per_launch, launches
     except Exception:
-        return None
+        return None, None, None
 
 
 class ClockSampler:
@@ -367,7 +372,10 @@ def run_gpu(args):
                    "n": n, "nnz": n * k, "algorithmic_bytes_per_step": nbytes,
                    "l2": "no flush: the 3.84 GB matrix stream exceeds the 126 MB L2 every step"},
         "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
-                     "traffic": load_traffic(), "peak_source": peak_src, "per_gpu": True,
+                     "traffic": load_traffic()[0] if world == 1 else None,     # the ncu capture is of the single-GPU step
+                     "traffic_per_launch": load_traffic()[1] if world == 1 else None, "launches_per_step": load_traffic()[2],
+                     "traffic_note": "achieved and traffic are per STEP = one (#>) = launches_per_step launches of the kernel",
+                     "peak_source": peak_src, "per_gpu": True,
                      "kernel": "spmv_tile_kernel<1024, EPI_NONE> (one launch per column panel, 2 panels at n = 10M)"},
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8 * nloc, "d2h_bytes_per_step": 8 * nloc,
                 "ms_per_step": e2e_s * 1e3, "api": "sla_spmv_host (pinned host buffers, per-rank slices)"},
