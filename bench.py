@@ -109,7 +109,10 @@ def cpu_baseline(threads, n_sample=2_000_000, reps=3):
     ora.time_matvec(A, x, 1, threads)
     sec = ora.time_matvec(A, x, reps, threads)
     gbs = spmv_bytes(n_sample, n_sample * K_CFG2) / sec / 1e9
-    return gbs, sec, f"config-2 family (uniform, 32 nnz/row) at n={n_sample} rows ({n_sample * K_CFG2} nnz), {reps} matvecs"
+    # the reference itself is single-threaded (cabal: no -threaded): the same product on ONE host thread, for context
+    sec1 = ora.time_matvec(A, x, 1, 1)
+    gbs1 = spmv_bytes(n_sample, n_sample * K_CFG2) / sec1 / 1e9
+    return gbs, sec, f"config-2 family (uniform, 32 nnz/row) at n={n_sample} rows ({n_sample * K_CFG2} nnz), {reps} matvecs", gbs1
 
 
 def run_reference(args):
@@ -360,9 +363,9 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        gbs, sec, sample = cpu_baseline(threads)
+        gbs, sec, sample, gbs1 = cpu_baseline(threads)
         cpu = {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
-               "seconds_per_matvec_on_sample": sec}
+               "seconds_per_matvec_on_sample": sec, "single_thread_value": gbs1}
     out = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
