@@ -36,3 +36,24 @@ def test_request_port_floor_of_cfg2():
     t_ms = req / (148 * 1.965e9) * 1e3
     assert 1.20 <= t_ms <= 1.23
     assert 0.50 <= rm.b_spmv(10_000_000, 320_000_000) / (t_ms * 1e-3) / 1e9 / 6534.8 <= 0.52
+
+
+def test_gather_microbenchmark_compiles(tmp_path):
+    """scripts/microbench/gather_paths.cu (the request-port probe of DESIGN.md §3.1) cross-compiles for sm_100a and its
+    SASS uses the three paths it claims to measure."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        import pytest
+
+        pytest.skip("nvcc not available")
+    exe = os.path.join(str(tmp_path), "gather_paths")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-o", exe,
+                           os.path.join(ROOT, "scripts", "microbench", "gather_paths.cu")])
+    cuobjdump = os.path.join(os.path.dirname(nvcc), "cuobjdump")
+    if os.path.exists(cuobjdump):
+        sass = subprocess.run([cuobjdump, "-sass", exe], capture_output=True, text=True).stdout
+        for mnemonic in ("LDG.E.NA", "LDGSTS", "UBLKCP"):
+            assert mnemonic in sass, mnemonic
