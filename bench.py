@@ -334,7 +334,8 @@ def run_gpu(args):
         extra["arnoldi_cfg4_gbs"] = b4bytes / s4 / 1e9
         del A4, Qd
     if "cfg5" in want:
-        # ---- config 5: (##) CSR 10M x 10M x dense 10M x 128 bf16 (single GPU: ## is not row-partitioned yet).
+        # ---- config 5: (##) CSR 10M x 10M x dense 10M x 128 bf16 (single GPU here; the row-partitioned (##) exists but has not
+        # been run on hardware yet, so it stays out of the default multi-GPU line).
         # K16 = block-structured family (tcgen05 tile path); U = uniform columns (gather kernel, L2-bound).
         if world == 1:
             k5 = 128

@@ -70,6 +70,7 @@ extern "C" void sla_finalize(sla_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   sla_p2p_free(c);
+  cudaFree(c->bfull); c->bfull = nullptr; c->bfull_bytes = 0;
   for (int k = 0; k < c->n_parked; ++k) cudaFree(c->parked[k]);
   c->n_parked = 0;
   if (c->nccl) sla_dist_detach(c);

@@ -45,6 +45,7 @@ struct sla_ctx {
   cudaEvent_t ev_copy[SLA_MAX_PANELS + 16];
   int spmv_tma;              // 0: LDG tile kernel; k > 0: TMA-staged persistent kernel with k CTAs per SM (env SLA_SPMV_TMA)
   const void* scal_owner;    // Krylov state whose recurrence scalars currently live in scal[]
+  void* bfull; size_t bfull_bytes;   // gathered dense right operand of a row-partitioned (##) (spmm.cu / dist.cu)
   struct sla_p2p* p2p;       // peer-memory all-reduce window (p2p.cu); null / disabled: NCCL
   void* parked[SLA_MAX_PARKED]; int n_parked;   // exchange windows of freed matrices (peers may still map them)
   char err[512];
@@ -71,6 +72,7 @@ struct sla_dist_info {
   int nseg; sla_xseg* seg;
   double* xfull;             // n doubles; only the remote entries this rank references are kept current
   int allgather;             // the plan is a plain all-gather of equal slices (collective decision)
+  int dense_equal;           // the host's collective decision as installed (allgather may be switched off by a transport choice)
   // dense plans are pipelined: the segments clipped to each column panel, exchanged panel by panel on
   // comm_stream while the kernels of the earlier panels run
   int pipelined;
@@ -284,6 +286,7 @@ sla_status sla_dist_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_loc
 sla_status sla_dist_exchange_panel(sla_ctx* c, const sla_csr* A, const double* x_local, int p);   // on comm_stream
 sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P);                                   // spmv.cu
 sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count);
+sla_status sla_dist_gather_rows(sla_ctx* c, const sla_csr* A, const void* local, void* full, int64_t k, int dtype);
 void sla_csr_free_dist(sla_csr* A);
 // peer-memory collectives (p2p.cu)
 bool sla_p2p_active(const sla_ctx* c);

@@ -164,7 +164,7 @@ extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int
   sla_csr_free_dist(A);
   sla_dist_info* d = new (std::nothrow) sla_dist_info();
   if (!d) return sla_fail(c, SLA_ERR_ALLOC, "set_dist alloc");
-  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0; d->pipelined = 0; d->pseg = nullptr; d->xwin = nullptr;
+  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0; d->dense_equal = 0; d->pipelined = 0; d->pseg = nullptr; d->xwin = nullptr;
   d->seg = new sla_xseg[nseg > 0 ? nseg : 1];
   for (int s = 0; s < nseg; ++s) {
     if (peer[s] < 0 || peer[s] >= c->world || peer[s] == c->rank || goff[s] < 0 || count[s] < 0 || goff[s] + count[s] > A->n ||
@@ -187,6 +187,7 @@ extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int
       return sla_fail(c, SLA_ERR_INVALID, "set_dist: all-gather needs equal row blocks in rank order");
     }
     d->allgather = 1;
+    d->dense_equal = 1;
   }
   A->dist = d;
   // EXPERIMENTAL (SLA_DIST_PIPELINE=1): pipeline the exchange under the column-panel kernels.  The panel count is
@@ -226,6 +227,33 @@ extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int
     }
   }
   A->dist = d;
+  return SLA_OK;
+}
+
+// (##) with a dense right operand on a row-partitioned matrix (NOT YET RUN ON HARDWARE): brings the rows of B this
+// rank's block references into `full` (n x k, row-major) — the x-exchange plan applied to k-wide rows.  `local` holds
+// this rank's rows [row0, row0 + m).  Dense equal-block plans use one all-gather, every other plan grouped send/recv.
+sla_status sla_dist_gather_rows(sla_ctx* c, const sla_csr* A, const void* local, void* full, int64_t k, int dtype) {
+  const sla_dist_info* d = A->dist;
+  if (!d || c->world <= 1) return SLA_OK;
+  const size_t esz = dtype == SLA_BF16 ? 2 : 8;
+  const ncclDataType_t nt = dtype == SLA_BF16 ? ncclBfloat16 : ncclDouble;
+  ncclComm_t comm = (ncclComm_t)c->nccl;
+  if (d->dense_equal) {
+    SLA_NCCL(c, ncclAllGather(local, full, (size_t)A->m * (size_t)k, nt, comm, c->stream));
+    return SLA_OK;
+  }
+  if (A->m > 0)
+    SLA_CUDA(c, cudaMemcpyAsync((char*)full + (size_t)d->row0 * (size_t)k * esz, local, (size_t)A->m * (size_t)k * esz,
+                                cudaMemcpyDeviceToDevice, c->stream));
+  SLA_NCCL(c, ncclGroupStart());
+  for (int s = 0; s < d->nseg; ++s) {
+    const sla_xseg& g = d->seg[s];
+    if (g.count == 0) continue;
+    if (g.dir == 0) SLA_NCCL(c, ncclRecv((char*)full + (size_t)g.goff * (size_t)k * esz, (size_t)g.count * (size_t)k, nt, g.peer, comm, c->stream));
+    else            SLA_NCCL(c, ncclSend((const char*)local + (size_t)(g.goff - d->row0) * (size_t)k * esz, (size_t)g.count * (size_t)k, nt, g.peer, comm, c->stream));
+  }
+  SLA_NCCL(c, ncclGroupEnd());
   return SLA_OK;
 }
 

@@ -163,17 +163,8 @@ static sla_status ensure_val_bf16(sla_ctx* c, const sla_csr* A) {
   return SLA_OK;
 }
 
-extern "C" sla_status sla_spmm_dense(sla_ctx* c, const sla_csr* A, const sla_dense* B, sla_dense* C) {
-  if (!c || !A || !B || !C) return SLA_ERR_INVALID;
-  if (A->dist) return sla_fail(c, SLA_ERR_INVALID, "## : row-partitioned operands are not supported yet");
-  if (!B->rowmajor || !C->rowmajor) return sla_fail(c, SLA_ERR_INVALID, "## : dense operands must be row-major blocks (sla_dense_create)");
-  if (A->n != B->rows) {    // matMatCheck | c1 == r2 ... | otherwise = error   SpMatrix.hs:790-797
-    snprintf(c->err, sizeof(c->err), "matMat : incompatible matrix sizes((%lld,%lld),(%lld,%lld))", (long long)A->m, (long long)A->n,
-             (long long)B->rows, (long long)B->cols);
-    return SLA_ERR_SIZE_MISMATCH;
-  }
-  if (C->rows != A->m || C->cols != B->cols) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "## : output block has the wrong shape");
-  if (B->dtype != C->dtype) return sla_fail(c, SLA_ERR_INVALID, "## : B and C must have the same element type");
+// the single-GPU product: A's column indices address rows of B directly
+static sla_status spmm_local(sla_ctx* c, const sla_csr* A, const sla_dense* B, sla_dense* C) {
   if (A->m == 0 || B->cols == 0) return SLA_OK;
   const int m = (int)A->m, k = (int)B->cols;
   const int64_t warps = A->m;
@@ -195,6 +186,35 @@ extern "C" sla_status sla_spmm_dense(sla_ctx* c, const sla_csr* A, const sla_den
   }
   SLA_LAUNCH_CHECK(c);
   return SLA_OK;
+}
+
+extern "C" sla_status sla_spmm_dense(sla_ctx* c, const sla_csr* A, const sla_dense* B, sla_dense* C) {
+  if (!c || !A || !B || !C) return SLA_ERR_INVALID;
+  if (!B->rowmajor || !C->rowmajor) return sla_fail(c, SLA_ERR_INVALID, "## : dense operands must be row-major blocks (sla_dense_create)");
+  // a row block of a distributed matrix multiplies the matching ROW SLICE of B: B holds rows [row0, row0 + m) of the n x k operand
+  const int64_t b_rows_expected = A->dist ? A->m : A->n;
+  if (b_rows_expected != B->rows) {    // matMatCheck | c1 == r2 ... | otherwise = error   SpMatrix.hs:790-797
+    snprintf(c->err, sizeof(c->err), "matMat : incompatible matrix sizes((%lld,%lld),(%lld,%lld))", (long long)A->m, (long long)A->n,
+             (long long)B->rows, (long long)B->cols);
+    return SLA_ERR_SIZE_MISMATCH;
+  }
+  if (C->rows != A->m || C->cols != B->cols) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "## : output block has the wrong shape");
+  if (B->dtype != C->dtype) return sla_fail(c, SLA_ERR_INVALID, "## : B and C must have the same element type");
+  if (!A->dist || c->world <= 1) return spmm_local(c, A, B, C);
+  // ---- row-partitioned (NOT YET RUN ON HARDWARE): gather the rows of B the block references, then the local product.
+  // Every rank takes part in the gather even when it has no rows.
+  const size_t esz = B->dtype == SLA_BF16 ? 2 : 8;
+  const size_t need = (size_t)A->n * (size_t)B->cols * esz;
+  if (c->bfull_bytes < need) {
+    SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->bfull); c->bfull = nullptr; c->bfull_bytes = 0;
+    if (cudaMalloc(&c->bfull, need ? need : 1) != cudaSuccess) { cudaGetLastError(); return sla_fail(c, SLA_ERR_ALLOC, "## : cudaMalloc failed for the gathered right operand"); }
+    c->bfull_bytes = need;
+  }
+  SLA_TRY(sla_dist_gather_rows(c, A, B->d, c->bfull, B->cols, B->dtype));
+  sla_dense view = *B;
+  view.rows = A->n; view.d = (double*)c->bfull;
+  return spmm_local(c, A, &view, C);
 }
 
 // =================================================================================================================
