@@ -45,6 +45,7 @@ foreign import ccall safe "sla_init"            c_init        :: CInt -> Ptr (Pt
 foreign import ccall safe "sla_finalize"        c_finalize    :: Ptr SlaCtx -> IO ()
 foreign import ccall safe "sla_last_error"      c_last_error  :: Ptr SlaCtx -> IO CString
 foreign import ccall safe "sla_csr_from_coo"    c_from_coo    :: Ptr SlaCtx -> Int64 -> Int64 -> Int64 -> Ptr Int64 -> Ptr Int64 -> Ptr Double -> Ptr (Ptr SlaCsr) -> IO Status
+foreign import ccall safe "sla_csr_dims"        c_csr_dims    :: Ptr SlaCsr -> Ptr Int64 -> Ptr Int64 -> Ptr Int64 -> IO Status
 foreign import ccall safe "sla_csr_transpose"   c_transpose   :: Ptr SlaCtx -> Ptr SlaCsr -> Ptr (Ptr SlaCsr) -> IO Status
 foreign import ccall safe "&sla_csr_free"       p_csr_free    :: FunPtr (Ptr SlaCsr -> IO ())
 foreign import ccall safe "sla_vec_from_host"   c_vec_from    :: Ptr SlaCtx -> Int64 -> Ptr Double -> Ptr (Ptr SlaVec) -> IO Status
@@ -162,6 +163,12 @@ normalize2 x@(DVector ctx@(Ctx c) fx) = do
   withForeignPtr fx $ \px -> withForeignPtr fz $ \pz -> c_normalize2 c px pz >>= check ctx "normalize2"
   return z
 
+-- | (nrows, ncols) of a device matrix
+dimM :: DMatrix -> IO (Int64, Int64)
+dimM (DMatrix _ fa) = withForeignPtr fa $ \pa -> alloca $ \pm -> alloca $ \pn -> alloca $ \pz -> do
+  _ <- c_csr_dims pa pm pn pz
+  (,) <$> peek pm <*> peek pn
+
 matvecWith :: String -> (Ptr SlaCtx -> Ptr SlaCsr -> Ptr SlaVec -> Ptr SlaVec -> IO Status) -> Int64 -> DMatrix -> DVector -> IO DVector
 matvecWith who f n (DMatrix ctx@(Ctx c) fa) (DVector _ fx) = do
   y@(DVector _ fy) <- newVec ctx n
@@ -169,10 +176,10 @@ matvecWith who f n (DMatrix ctx@(Ctx c) fa) (DVector _ fx) = do
   return y
 
 -- | aa #> v   (Common.hs:242-250)          v <# aa   (Common.hs:253-256)
-(#>) :: (DMatrix, Int64) -> DVector -> IO DVector
-(aa, m) #> v = matvecWith "matVec" c_spmv m aa v
-(<#) :: DVector -> (DMatrix, Int64) -> IO DVector
-v <# (aa, n) = matvecWith "vecMat" c_spmvT n aa v
+(#>) :: DMatrix -> DVector -> IO DVector
+aa #> v = do { (m, _) <- dimM aa; matvecWith "matVec" c_spmv m aa v }
+(<#) :: DVector -> DMatrix -> IO DVector
+v <# aa = do { (_, n) <- dimM aa; matvecWith "vecMat" c_spmvT n aa v }
 
 transpose :: DMatrix -> IO DMatrix
 transpose (DMatrix ctx@(Ctx c) fa) = withForeignPtr fa $ \pa -> alloca $ \pp -> do
