@@ -99,12 +99,41 @@ def _worker(rank, world, port, kind_name, n, k, band, ret):
         y_local = Aloc.matVec(xs).toDenseListSV()
         ys = [None] * world
         dist.all_gather_object(ys, y_local)
+        # the same plan applied to k-wide rows is the gather of the dense right operand of a row-partitioned (##)
+        # (sla_dist_gather_rows): every B row the block references must arrive, and the local product must equal the
+        # rows of the single-process product bit for bit
+        kk = 3
+        B_full_true = np.random.default_rng(99).standard_normal((n, kk))
+        B_local = B_full_true[r0:r1].copy()
+        B_full = np.full((n, kk), np.nan)
+        B_full[r0:r1] = B_local
+        reqs, bufs = [], []
+        for d, q, off, cnt in segs:
+            if d == 1:
+                reqs.append(dist.isend(torch.from_numpy(B_local[off - r0: off - r0 + cnt].copy()), q))
+        for d, q, off, cnt in segs:
+            if d == 0:
+                t = torch.empty((cnt, kk), dtype=torch.float64)
+                bufs.append((off, cnt, t))
+                reqs.append(dist.irecv(t, q))
+        for r in reqs:
+            r.wait()
+        for off, cnt, t in bufs:
+            B_full[off: off + cnt] = t.numpy()
+        assert not np.isnan(B_full[touched]).any(), "the plan left a referenced row of B un-gathered"
+        assert np.array_equal(B_full[touched], B_full_true[touched])
+        Bo = ora.SpMatrix.fromListDenseSM(n, np.where(np.isnan(B_full), 0.0, B_full).T.reshape(-1))
+        c_local = Aloc.matMat(Bo).toDense()
+        cs = [None] * world
+        dist.all_gather_object(cs, c_local)
         plans = [None] * world
         dist.all_gather_object(plans, segs)
         if rank == 0:
             Afull = ora.SpMatrix.synth(kind, n, k, seed, band)
             yref = Afull.matVec(ora.SpVector.synth(seed + 1, n)).toDenseListSV()
             ok = np.concatenate(ys).tobytes() == yref.tobytes()
+            cref = Afull.matMat(ora.SpMatrix.fromListDenseSM(n, B_full_true.T.reshape(-1))).toDense()
+            ok = ok and np.ascontiguousarray(np.concatenate(cs, axis=0)).tobytes() == np.ascontiguousarray(cref).tobytes()
             for p in range(world):
                 for d, q, off, cnt in plans[p]:
                     ok = ok and (1 - d, p, off, cnt) in plans[q]
