@@ -104,6 +104,11 @@ sla_status sla_csr_p2p_export(sla_ctx*, sla_csr*, void* handle64);
 sla_status sla_csr_p2p_attach(sla_ctx*, sla_csr*, const void* handles /* world x 64 bytes */);
 sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on /* 0 off, 1 push kernel, 2 copy engines + arrival-order panels */);
 int        sla_csr_p2p_mode(const sla_csr*);      /* the mode in force (2 falls back to 1 when the plan is not dense / equal-block) */
+/* transposeSM of a row-partitioned square matrix (all-to-all of entries; starts = world + 1 global row offsets, the same on
+ * every rank): *out is this rank's row block of the transpose; give it an exchange plan like any block, then hand it to A
+ * with sla_csr_attach_transpose so that (<#) and CGNE on the distributed A use it (A owns it afterwards). */
+sla_status sla_csr_transpose_dist(sla_ctx*, const sla_csr* A, const int64_t* starts, sla_csr** out);
+sla_status sla_csr_attach_transpose(sla_ctx*, sla_csr* A, sla_csr* T);
 sla_status sla_vec_generate_slice(sla_ctx*, int64_t i0, int64_t n, uint64_t seed, sla_vec** out);
 sla_status sla_csr_dims(const sla_csr*, int64_t* m, int64_t* n, int64_t* nnz);
 sla_status sla_csr_to_host(sla_ctx*, const sla_csr*, int32_t* row_ptr, int32_t* col_idx, double* val);

@@ -220,7 +220,7 @@ extern "C" sla_status sla_spmv(sla_ctx* c, const sla_csr* A, const sla_vec* x, s
 
 extern "C" sla_status sla_spmvT(sla_ctx* c, const sla_csr* A, const sla_vec* x, sla_vec* y) {
   if (!c || !A || !x || !y) return SLA_ERR_INVALID;
-  if (A->dist) return sla_fail(c, SLA_ERR_INVALID, "vecMat : the transpose of a row-partitioned matrix is not supported");
+  if (A->dist && !A->T) return sla_fail(c, SLA_ERR_INVALID, "vecMat : attach the distributed transpose of the row-partitioned matrix first");
   if (A->m != x->n) {   // vecMatSD | n == nr ... | otherwise = error   Common.hs:254-256
     snprintf(c->err, sizeof(c->err), "vecMat : mismatching dimensions (%lld,%lld)", (long long)x->n, (long long)A->m);
     return SLA_ERR_SIZE_MISMATCH;

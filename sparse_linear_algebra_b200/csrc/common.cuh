@@ -286,6 +286,11 @@ sla_status sla_dist_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_loc
 sla_status sla_dist_exchange_panel(sla_ctx* c, const sla_csr* A, const double* x_local, int p);   // on comm_stream
 sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P);                                   // spmv.cu
 sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count);
+sla_status sla_dist_allgather_i32(sla_ctx* c, const int* d_send, int* d_recv, int count);
+sla_status sla_dist_group_begin(sla_ctx* c);
+sla_status sla_dist_group_end(sla_ctx* c);
+sla_status sla_dist_send(sla_ctx* c, const void* p, size_t count, int bytes8, int peer);
+sla_status sla_dist_recv(sla_ctx* c, void* p, size_t count, int bytes8, int peer);
 sla_status sla_dist_gather_rows(sla_ctx* c, const sla_csr* A, const void* local, void* full, int64_t k, int dtype);
 void sla_csr_free_dist(sla_csr* A);
 // peer-memory collectives (p2p.cu)

@@ -135,6 +135,24 @@ sla_status sla_dist_finish_reduction(sla_ctx* c, int nv, int fin, int dst) {
   return SLA_OK;
 }
 
+// ---- helpers of the distributed transpose (dist_transpose.cu keeps no NCCL types of its own) --------------------
+sla_status sla_dist_allgather_i32(sla_ctx* c, const int* d_send, int* d_recv, int count) {
+  if (c->world <= 1) return SLA_OK;
+  SLA_NCCL(c, ncclAllGather(d_send, d_recv, (size_t)count, ncclInt32, (ncclComm_t)c->nccl, c->stream));
+  return SLA_OK;
+}
+sla_status sla_dist_group_begin(sla_ctx* c) { SLA_NCCL(c, ncclGroupStart()); return SLA_OK; }
+sla_status sla_dist_group_end(sla_ctx* c) { SLA_NCCL(c, ncclGroupEnd()); return SLA_OK; }
+// bytes8 = 0: int32 elements, 1: doubles
+sla_status sla_dist_send(sla_ctx* c, const void* p, size_t count, int bytes8, int peer) {
+  SLA_NCCL(c, ncclSend(p, count, bytes8 ? ncclDouble : ncclInt32, peer, (ncclComm_t)c->nccl, c->stream));
+  return SLA_OK;
+}
+sla_status sla_dist_recv(sla_ctx* c, void* p, size_t count, int bytes8, int peer) {
+  SLA_NCCL(c, ncclRecv(p, count, bytes8 ? ncclDouble : ncclInt32, peer, (ncclComm_t)c->nccl, c->stream));
+  return SLA_OK;
+}
+
 sla_status sla_dist_allreduce_int(sla_ctx* c, int* d_val, int count) {
   if (c->world <= 1) return SLA_OK;
   SLA_NCCL(c, ncclAllReduce(d_val, d_val, (size_t)count, ncclInt, ncclSum, (ncclComm_t)c->nccl, c->stream));

@@ -186,8 +186,9 @@ extern "C" sla_status sla_cgne_init(sla_ctx* c, const sla_csr* A, const sla_vec*
   if (!out) return SLA_ERR_INVALID;
   *out = nullptr;
   SLA_TRY(check_system(c, "cgneInit", A, b, x0));
-  if (A->dist) return sla_fail(c, SLA_ERR_INVALID, "cgneInit: the transpose of a row-partitioned matrix is not supported");
-  SLA_TRY(ensure_transpose(c, A));
+  // a row-partitioned matrix needs its distributed transpose attached first (sla_csr_transpose_dist + sla_csr_attach_transpose)
+  if (A->dist && !A->T) return sla_fail(c, SLA_ERR_INVALID, "cgneInit: attach the distributed transpose of the row-partitioned matrix first");
+  if (!A->dist) SLA_TRY(ensure_transpose(c, A));
   sla_krylov* st = nullptr;
   SLA_TRY(krylov_alloc(c, SLA_CGNE_, A->m, false, &st));
   sla_status s = init_residual(c, A, b, x0, st, st->r->d, st->t1->d, st->t1->d);
@@ -200,9 +201,9 @@ extern "C" sla_status sla_cgne_init(sla_ctx* c, const sla_csr* A, const sla_vec*
 
 extern "C" sla_status sla_cgne_step(sla_ctx* c, const sla_csr* A, sla_krylov* st) {
   if (!c || !A || !st || st->kind != SLA_CGNE_) return SLA_ERR_INVALID;
-  if (A->dist) return sla_fail(c, SLA_ERR_INVALID, "cgneStep: the transpose of a row-partitioned matrix is not supported");
-  if (A->m != st->n || A->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgneStep: dimensions differ");
-  SLA_TRY(ensure_transpose(c, A));
+  if (A->dist && !A->T) return sla_fail(c, SLA_ERR_INVALID, "cgneStep: attach the distributed transpose of the row-partitioned matrix first");
+  if (A->m != st->n || csr_xdim(A) != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgneStep: dimensions differ");
+  if (!A->dist) SLA_TRY(ensure_transpose(c, A));
   const int64_t n = st->n;
   double *x = st->x->d, *r = st->r->d, *p = st->p->d, *ap = st->t0->d, *atr = st->t1->d;
   c->scal_owner = st;

@@ -192,6 +192,22 @@ def distribute(ctx, A, starts):
     return A
 
 
+def transpose_distributed(ctx, A):
+    """transposeSM (SpMatrix.hs:717-718) of a row-partitioned square matrix: an all-to-all of entries inside the library
+    (csrc/dist_transpose.cu), then the usual exchange plan for the new block.  The result is attached to A as the cached
+    transpose, so `x <# A` and cgneInit / cgneStep work on the distributed A; A owns it (the returned wrapper borrows).
+    Collective.  NOT YET RUN ON HARDWARE."""
+    starts = list(A.row_starts)
+    arr = (C.c_int64 * len(starts))(*starts)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.sla_csr_transpose_dist(ctx.h, A.h, arr, C.byref(h)))
+    T = SpMatrix(ctx, h, owns=False)
+    distribute(ctx, T, starts)
+    ctx.check(ctx.lib.sla_csr_attach_transpose(ctx.h, A.h, T.h))
+    T._owner = A                     # the handle lives as long as A does
+    return T
+
+
 def generate_distributed(ctx, kind, n, nnz_per_row, seed, band=0):
     """Rank-local block of the n x n synthetic family (include/sla_synth.h), row-partitioned over the job."""
     import torch.distributed as dist

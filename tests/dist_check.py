@@ -94,6 +94,25 @@ def main():
             Cl = A.matMat(sla.DenseMatrix.fromHost(Bh[r0:r1])).toHost()
             Co = Ao.matMat(ora.SpMatrix.fromListDenseSM(n, Bh.T.reshape(-1))).toDense()
             check(f"{name}: row-partitioned (##) bit-exact", Cl.tobytes() == np.ascontiguousarray(Co[r0:r1]).tobytes())
+        # transposeSM / (<#) / CGNE on the row-partitioned matrix (same gate: not yet seen green on hardware)
+        if name in ("uniform", "banded", "ragged") and os.environ.get("SLA_DIST_CHECK_EXPERIMENTAL") == "1":
+            T = sd.transpose_distributed(ctx, A)
+            rpT, ciT, vaT = T.toCSR()
+            rpo, cio, vao = Ao.transpose().toCSR()
+            lo_, hi_ = int(rpo[r0]), int(rpo[r1])
+            check(f"{name}: distributed transpose row_ptr", np.array_equal(rpT.astype(np.int64), np.asarray(rpo[r0:r1 + 1], dtype=np.int64) - lo_))
+            check(f"{name}: distributed transpose col", np.array_equal(ciT.astype(np.int64), np.asarray(cio[lo_:hi_], dtype=np.int64)))
+            check(f"{name}: distributed transpose val", np.asarray(vaT).tobytes() == np.ascontiguousarray(vao[lo_:hi_], dtype=np.float64).tobytes())
+            z = A.vecMat(x, out=sla.SpVector.zeroSV(r1 - r0)).toDenseListSV()
+            zo = Ao.vecMat(xo).toDenseListSV()
+            check(f"{name}: row-partitioned (<#) bit-exact", z.tobytes() == zo[r0:r1].tobytes())
+            st = sla.cgneInit(A, b, sla.SpVector.zeroSV(r1 - r0))
+            sto = ora.cgneInit(Ao, bo, ora.SpVector.mkSpVR(n, np.zeros(n)))
+            for it in range(3):
+                sla.cgneStep(A, st)
+                sto = ora.cgneStep(Ao, sto)
+                xg, xr = st.x.toDenseListSV(), sto.x.toDenseListSV()
+                check(f"{name}: cgneStep iterate {it}", np.abs(xg - xr[r0:r1]).max() <= 1e-10 * max(np.abs(xr).max(), 1e-300))
         # arnoldi: H equals the oracle's while the basis is well conditioned
         Qd, H, brk = sla.arnoldi(A, x, 6)
         Qo, Ho = ora.arnoldi(Ao, xo, 6)
