@@ -172,3 +172,52 @@ def test_exchange_protocol_model(world):
         for r in range(world):
             for seq, got in outs[r]:
                 assert got == {t: (t + 1) * 1000 + seq for t in range(world) if t != r}, f"rank {r}, exchange {seq}"
+
+
+# ---- mode 2 (copy-engine all-gather consumed in arrival order): each rank is TWO actors — the compute stream, which
+# records "x is final" at the start of (#>) number seq and then walks the panels waiting for one source at a time, and
+# the comm stream, which after that event copies the local block to r+1, r+2, ... each followed by a flag.
+
+def _arrival_compute(rank, world, nex, win, ev, out):
+    for seq in range(1, nex + 1):
+        ev[rank] = seq                                   # cudaEventRecord(ev_x0): earlier panel kernels are done
+        yield
+        b = seq & 1
+        got = {}
+        for k in range(1, world):
+            src = (rank - k) % world
+            while win[rank]["flag"][src] < seq:          # p2p_wait_kernel
+                yield
+            got[src] = win[rank]["buf"][b][src]          # the panel kernel reading xfull
+            yield
+        out.append((seq, got))
+
+
+def _arrival_comm(rank, world, nex, win, ev):
+    for seq in range(1, nex + 1):
+        while ev[rank] < seq:                            # cudaStreamWaitEvent(comm_stream, ev_x0)
+            yield
+        b = seq & 1
+        for k in range(1, world):
+            q = (rank + k) % world
+            win[q]["buf"][b][rank] = (rank + 1) * 1000 + seq      # cudaMemcpyAsync to the peer window
+            yield
+            win[q]["flag"][rank] = seq                            # p2p_flag_kernel
+            yield
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_arrival_order_protocol_model(world):
+    for seed in range(40):
+        rng = random.Random(seed * 613 + world)
+        nex = 10
+        win = [{"buf": [[None] * world for _ in range(2)], "flag": [0] * world} for _ in range(world)]
+        ev = [0] * world
+        outs = [[] for _ in range(world)]
+        gens = [_arrival_compute(r, world, nex, win, ev, outs[r]) for r in range(world)]
+        gens += [_arrival_comm(r, world, nex, win, ev) for r in range(world)]
+        _run(gens, rng)
+        for r in range(world):
+            assert [s for s, _ in outs[r]] == list(range(1, nex + 1))
+            for seq, got in outs[r]:
+                assert got == {t: (t + 1) * 1000 + seq for t in range(world) if t != r}, f"rank {r}, exchange {seq}"
