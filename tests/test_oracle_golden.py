@@ -309,3 +309,66 @@ def test_synth_rows(o):
     assert cols.tolist() == [0, 1, 4]
     a = o.SpMatrix.synth(o.GEN_LAPLACE2D, 16, 5, 0, 4)
     assert a.nnz == 5 * 16 - 4 * 4
+
+
+# ---- README.md:208-227: `iterate (bicgstabStep amat r0hat) initState !! 20` / `iterate (cgsStep amat rhat) initState !! 20`
+# are printed as 1.50, -2.00, 1.00.  A DISCRIMINATING observable for the summation order: with the strict
+# left fold that base >= 4.16 gives the derived Foldable (((0 + a0) + a1) + a2), BiCGSTAB converges at step 3, keeps
+# squaring the residual down and meets the exact "lucky breakdown" s = r - alpha * A p = 0 at step 18 (omega = 0 / 0):
+# x is NaN from then on, as the reference's unguarded recurrence dictates.  With a0 + (a1 + a2) the breakdown does not occur
+# within 25 steps.  Without GHC the README printout cannot be re-run; this test pins what the restatement does and shows
+# the sensitivity, so that whoever has GHC can settle the order with one GHCi line.
+def test_readme_twenty_steps_is_order_sensitive(o):
+    amat = o.SpMatrix.fromListSM(*F.AMAT)
+    b = _vr(o, F.AMAT_B)
+    x0 = o.SpVector.fromListSV(3, [])
+    rhat = b - amat.matVec(x0)
+    st = o.bicgsInit(amat, b, x0)
+    first_nan = None
+    for k in range(1, 21):
+        st = o.bicgstabStep(amat, rhat, st)
+        if first_nan is None and np.isnan(st.x.toDenseListSV()).any():
+            first_nan = k
+        if k == 17:
+            np.testing.assert_allclose(st.x.toDenseListSV(), F.AMAT_X, atol=1e-12)
+    assert first_nan == 18
+    st = o.cgsInit(amat, b, x0)
+    for _ in range(20):
+        st = o.cgsStep(amat, rhat, st)
+    np.testing.assert_allclose(st.x.toDenseListSV(), F.AMAT_X, atol=1e-12)      # CGS: 20 steps, as printed
+
+    # the same recurrence in plain Python floats with both associations of the 3-term sums
+    A = {0: {0: 2.0}, 1: {0: 4.0, 1: 3.0, 2: 2.0}, 2: {2: 5.0}}
+    bb = [3.0, 2.0, 5.0]
+
+    def run(right):
+        def fold(xs):
+            acc = 0.0
+            for v in (reversed(xs) if right else xs):
+                acc = (v + acc) if right else (acc + v)
+            return acc
+
+        dot = lambda u, v: fold([a * c for a, c in zip(u, v)])
+        mv = lambda v: [fold([A[i][j] * v[j] for j in sorted(A[i])]) for i in range(3)]
+        x, r = [0.0] * 3, list(bb)
+        p, r0 = list(r), list(r)
+        for it in range(1, 26):
+            aap = mv(p)
+            den = dot(aap, r0)
+            if den == 0.0:
+                return it
+            al = dot(r, r0) / den
+            s = [ri - al * ai for ri, ai in zip(r, aap)]
+            aas = mv(s)
+            den = dot(aas, aas)
+            if den == 0.0:
+                return it
+            om = dot(aas, s) / den
+            x = [(xi + al * pi) + om * si for xi, pi, si in zip(x, p, s)]
+            rn = [si - om * ai for si, ai in zip(s, aas)]
+            be = dot(rn, r0) / dot(r, r0) * al / om
+            p = [ri + be * (pi - om * ai) for ri, pi, ai in zip(rn, p, aap)]
+            r = rn
+        return None
+
+    assert run(right=False) == 18 and run(right=True) is None
