@@ -302,6 +302,7 @@ bool sla_xwin_active(const sla_csr* A);
 int sla_xwin_mode(const sla_csr* A);                                                             // 0 off, 1 push kernel, 2 arrival order
 sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_local);
 sla_status sla_p2p_arrival_wait(sla_ctx* c, const sla_csr* A, int src);
+sla_status sla_p2p_arrival_end(sla_ctx* c);
 sla_status sla_p2p_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local);
 void sla_xwin_free(sla_csr* A);
 void sla_csr_free_bsr(sla_csr* A);

@@ -380,7 +380,15 @@ sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_l
     p2p_flag_kernel<<<1, 1, 0, c->comm_stream>>>(reinterpret_cast<unsigned long long*>(X->peer[q]) + c->rank, X->seq);
     SLA_LAUNCH_CHECK(c);
   }
+  SLA_CUDA(c, cudaEventRecord(c->ev_panel[0], c->comm_stream));       // "my outgoing copies have read x_local"
   d->xfull = reinterpret_cast<double*>(X->win + off);
+  return SLA_OK;
+}
+
+// mode 2, last step (compute stream): whatever follows the (#>) may overwrite x_local, so it must wait until the copy
+// engines have finished reading it (the panel kernels only wait for INCOMING blocks)
+sla_status sla_p2p_arrival_end(sla_ctx* c) {
+  SLA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_panel[0], 0));
   return SLA_OK;
 }
 

@@ -717,7 +717,7 @@ static sla_status spmv_launch_arrival(sla_ctx* c, const sla_csr* A, const double
     a.yin = k == 0 ? nullptr : ybuf; a.y = ybuf;
     SLA_TRY(launch_any(c, k + 1 == W ? epi : EPI_NONE, k > 0, true, a));
   }
-  return SLA_OK;
+  return sla_p2p_arrival_end(c);
 }
 
 // y = A x with an optional fused epilogue.  u1 is reserved (EPI_DOT2_YY uses y itself).
