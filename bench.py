@@ -351,6 +351,22 @@ def run_gpu(args):
                 extra[f"spmm_cfg5_{tag}_tflops"] = 2 * A5.nnz * k5 / (ms5 * 1e-3) / 1e12
                 del A5
             del B5, C5
+        elif os.environ.get("SLA_BENCH_DIST_SPMM") == "1":
+            # row-partitioned (##): written after the round-1 GPU budget was spent, so it is opt-in and can never cost the line
+            try:
+                k5 = 128
+                A5 = gen(sla.GEN_BLOCK16, n, 32, 0x5EED0005)
+                s5 = A5.row_starts
+                m5 = s5[rank + 1] - s5[rank]
+                B5 = sla.DenseMatrix.generate(m5, k5, 0x5EED0055 + rank, sla.BF16)      # this rank's row slice of B
+                C5 = sla.DenseMatrix.zeros(m5, k5, sla.BF16)
+                ms5, _ = timed(lambda: A5.matMat(B5, out=C5), 5, 1)
+                b5 = 6 * n * 32 + 4 * (n + 1) + 4 * n * k5
+                extra["spmm_cfg5_k16_dist_ms"] = ms5
+                extra["spmm_cfg5_k16_dist_gbs"] = b5 / (ms5 * 1e-3) / 1e9
+                del A5, B5, C5
+            except Exception as e:
+                extra["spmm_cfg5_dist_error"] = str(e)[:200]
 
     if rank != 0:
         if dist is not None:
