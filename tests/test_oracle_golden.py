@@ -372,3 +372,14 @@ def test_readme_twenty_steps_is_order_sensitive(o):
         return None
 
     assert run(right=False) == 18 and run(right=True) is None
+
+
+# ---- LibSpec.hs:81-84 "permutPairsSM : permutation matrices are orthogonal": pm0 #~#^ pm0 == eye 3, pm0 #~^# pm0 == eye 3
+# (#~#^ = sparsifySM (a ## transpose b), #~^# = sparsifySM (transpose a ## b), SpMatrix.hs:820-840).  permutPairsSM 3
+# [(0,2),(1,2)] swaps rows 0,2 then 1,2 of eye 3 (SpMatrix.hs:171-174): rows e2, e0, e1.
+def test_permutation_orthogonal_via_sparsified_products(o):
+    pm0 = o.SpMatrix.fromListSM((3, 3), [(0, 2, 1.0), (1, 0, 1.0), (2, 1, 1.0)])
+    full = pm0.matMat(pm0.transpose())
+    assert full.nnz == 9                                  # (##) keeps the explicit zeros ...
+    assert full.sparsifySM() == o.SpMatrix.eye(3)         # ... and the sparsified product is exactly the identity
+    assert pm0.transpose().matMat(pm0).sparsifySM() == o.SpMatrix.eye(3)
