@@ -115,6 +115,28 @@ def cpu_baseline(threads, n_sample=2_000_000, reps=3):
     return gbs, sec, f"config-2 family (uniform, 32 nnz/row) at n={n_sample} rows ({n_sample * K_CFG2} nnz), {reps} matvecs", gbs1
 
 
+def scipy_sanity(n_sample=500_000):
+    """Third leg of BASELINE.md §4: scipy's CSR product (one thread) on the same family — an implementation that shares
+    no code with the oracle.  Returns GB/s of algorithmic bytes, or None when scipy is unavailable."""
+    try:
+        import scipy.sparse as sp
+
+        from oracle import oracle as ora
+
+        A = ora.SpMatrix.synth(ora.GEN_UNIFORM, n_sample, K_CFG2, SEED_CFG2)
+        rp, ci, va = A.toCSR()
+        M = sp.csr_matrix((np.asarray(va), np.asarray(ci), np.asarray(rp)), shape=(n_sample, n_sample))
+        x = np.asarray(ora.SpVector.synth(SEED_CFG2 + 1, n_sample).toDenseListSV())
+        M @ x
+        t0 = time.perf_counter()
+        for _ in range(3):
+            M @ x
+        sec = (time.perf_counter() - t0) / 3
+        return spmv_bytes(n_sample, n_sample * K_CFG2) / sec / 1e9
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for the path (oracle port; the Haskell cannot be
     built here: no GHC), all host threads, each step a bounded sample of config 2."""
@@ -382,7 +404,7 @@ def run_gpu(args):
         threads = os.cpu_count() or 1
         gbs, sec, sample, gbs1 = cpu_baseline(threads)
         cpu = {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
-               "seconds_per_matvec_on_sample": sec, "single_thread_value": gbs1}
+               "seconds_per_matvec_on_sample": sec, "single_thread_value": gbs1, "scipy_csr_single_thread_value": scipy_sanity()}
     out = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
