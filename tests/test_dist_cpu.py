@@ -165,3 +165,49 @@ def test_row_partitioned_spmv_gloo(ora, kind, n, k, band):
         assert max(recv_bytes) <= 8 * band               # halo only
     if kind == "GEN_LAPLACE2D":
         assert recv_bytes == [8 * band] * 2              # one grid line from the neighbour
+
+
+# ---- property test of the planner (hypothesis): for ANY partition and ANY per-rank column ranges the plans of the ranks
+# are mutually consistent (every send has its receive), never self-directed, stay inside the sender's block, and deliver
+# every remote column a rank references.
+def test_plan_exchange_properties():
+    from hypothesis import given, settings, strategies as st
+
+    from sparse_linear_algebra_b200.dist import densify_needs, plan_exchange, row_partition
+
+    @st.composite
+    def cases(draw):
+        world = draw(st.integers(2, 8))
+        n = draw(st.integers(world, 400))
+        starts = row_partition(n, world)
+        needs = []
+        for _ in range(world):
+            if draw(st.booleans()) and draw(st.integers(0, 9)) == 0:
+                needs.append((0, -1))                       # a block without entries
+            else:
+                lo = draw(st.integers(0, n - 1))
+                needs.append((lo, draw(st.integers(lo, n - 1))))
+        return world, n, starts, needs
+
+    @settings(max_examples=300, deadline=None)
+    @given(cases())
+    def check(case):
+        world, n, starts, needs0 = case
+        for needs in (needs0, densify_needs(starts, needs0)[0]):
+            plans = [plan_exchange(r, starts, needs) for r in range(world)]
+            for r, pl in enumerate(plans):
+                got = np.zeros(n, bool)
+                got[starts[r]:starts[r + 1]] = True          # the own slice is read in place
+                for d, q, off, cnt in pl:
+                    assert q != r and cnt > 0 and 0 <= off and off + cnt <= n
+                    assert (1 - d, r, off, cnt) in plans[q]
+                    if d == 1:
+                        assert starts[r] <= off and off + cnt <= starts[r + 1]
+                    else:
+                        assert starts[q] <= off and off + cnt <= starts[q + 1]
+                        got[off:off + cnt] = True
+                lo, hi = needs[r]
+                if hi >= lo:
+                    assert got[lo:hi + 1].all(), "a referenced column is neither local nor received"
+
+    check()
