@@ -151,6 +151,10 @@ sla_status sla_cgne_init(sla_ctx*, const sla_csr* A, const sla_vec* b, const sla
 sla_status sla_cgne_step(sla_ctx*, const sla_csr* A, sla_krylov* st);                                           /* cgneStep :868-878 */
 sla_status sla_krylov_get(sla_ctx*, const sla_krylov*, int field, double* host_out);                            /* _x / _r / _p / _u */
 sla_status sla_krylov_view(sla_ctx*, const sla_krylov*, int field, const sla_vec** view);                       /* borrowed device view */
+/* The steps above advance the record IN PLACE.  The reference's steps are pure functions (`iterate (bicgstabStep aa r0hat)
+ * st0 !! 20`, README.md:208, keeps st0 usable): sla_krylov_clone makes the deep copy a pure `step` needs (clone, then advance
+ * the clone — what hs/Numeric/LinearAlgebra/Sparse/B200.hs does). */
+sla_status sla_krylov_clone(sla_ctx*, const sla_krylov* st, sla_krylov** out);
 void       sla_krylov_free(sla_krylov*);
 
 typedef struct {
@@ -158,7 +162,7 @@ typedef struct {
   double tol_abs;        /* tolAbs = 1e-6  Sparse.hs:1035 */
   double tol_rel;        /* tolRel = 1e-4  Sparse.hs:1036 */
   int    true_residual;  /* 1: ||A x - b|| recomputed (reference behaviour, Sparse.hs:1041); 0: recurrence residual ||r|| */
-  int    check_every;    /* 1: test every iteration (reference) */
+  int    check_every;    /* 1: test every iteration (reference); sla_gmres only: < 0 = no stopping test, run max_iters steps */
 } sla_solve_opts;
 void sla_solve_opts_default(sla_solve_opts*);
 

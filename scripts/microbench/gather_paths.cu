@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -31,6 +32,7 @@ __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
 // share = lanes per 128-byte line (1, 2 or 4): lanes of a group get the same line, different doubles inside it
 __global__ void make_idx(int* idx, int64_t n, int64_t table, int share) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (share == 0) { idx[i] = (int)(splitmix64((uint64_t)i * 0x9E37ull + 777u) % (uint64_t)table); continue; }   // any double of the table
     const int64_t group = i / share;
     const int64_t line = (int64_t)(splitmix64((uint64_t)group * 0x9E37ull + 12345u) % (uint64_t)(table / 16));
     idx[i] = (int)(line * 16 + (i % share) * (16 / share));
@@ -117,6 +119,59 @@ __global__ void __launch_bounds__(THREADS) k_bulk16(const int* __restrict__ idx,
   if (acc == -1.0) out[0] = acc;
 }
 
+
+// texture path: tex1Dfetch<int2> over the same linear table (TEX pipe of L1TEX instead of the LSU pipe)
+__global__ void __launch_bounds__(THREADS) k_tex(const int* __restrict__ idx, cudaTextureObject_t tex, double* out) {
+  const int64_t base = (int64_t)blockIdx.x * TILE;
+  int c[PER];
+#pragma unroll
+  for (int it = 0; it < PER; ++it) c[it] = ldg_stream(idx + base + it * THREADS + threadIdx.x);
+  double acc = 0.0;
+#pragma unroll
+  for (int it = 0; it < PER; ++it) {
+    const int2 v = tex1Dfetch<int2>(tex, c[it]);
+    acc += __hiloint2double(v.y, v.x);
+  }
+  if (acc == -1.0) out[0] = acc;
+}
+
+// half the gathers through LDG, half through TEX (do the two pipes add up?)
+__global__ void __launch_bounds__(THREADS) k_mix(const int* __restrict__ idx, const double* __restrict__ x, cudaTextureObject_t tex, double* out) {
+  const int64_t base = (int64_t)blockIdx.x * TILE;
+  int c[PER];
+#pragma unroll
+  for (int it = 0; it < PER; ++it) c[it] = ldg_stream(idx + base + it * THREADS + threadIdx.x);
+  double acc = 0.0;
+#pragma unroll
+  for (int it = 0; it < PER; ++it) {
+    if (it & 1) { const int2 v = tex1Dfetch<int2>(tex, c[it]); acc += __hiloint2double(v.y, v.x); }
+    else acc += ldg_na(x + c[it]);
+  }
+  if (acc == -1.0) out[0] = acc;
+}
+
+// shared-memory window: every CTA stages SLICE doubles of the table (coalesced 16-byte loads) and serves `tiles` tiles of
+// random 8-byte gathers from it — the banded-family design question: what does a gather cost once x sits in shared memory?
+constexpr int SM_THREADS = 1024;
+__global__ void __launch_bounds__(SM_THREADS) k_smem(const int* __restrict__ idx, const double* __restrict__ x, double* out,
+                                                     int slice, int tiles_per_cta) {
+  extern __shared__ __align__(16) double win[];
+  const double2* src = reinterpret_cast<const double2*>(x + (size_t)blockIdx.x * slice);
+  for (int i = threadIdx.x; i < slice / 2; i += SM_THREADS) reinterpret_cast<double2*>(win)[i] = src[i];
+  __syncthreads();
+  double acc = 0.0;
+  const int mask = slice - 1;
+  for (int t = 0; t < tiles_per_cta; ++t) {
+    const int64_t base = ((int64_t)blockIdx.x * tiles_per_cta + t) * (SM_THREADS * PER);
+    int c[PER];
+#pragma unroll
+    for (int it = 0; it < PER; ++it) c[it] = ldg_stream(idx + base + it * SM_THREADS + threadIdx.x);
+#pragma unroll
+    for (int it = 0; it < PER; ++it) acc += win[c[it] & mask];
+  }
+  if (acc == -1.0) out[0] = acc;
+}
+
 template <class K>
 static double time_kernel(K kernel, const int* idx, const double* x, double* out, int64_t gathers, int reps) {
   const unsigned grid = (unsigned)(gathers / TILE);
@@ -160,6 +215,53 @@ int main(int argc, char** argv) {
     else ms = time_kernel(k_bulk16, idx, x, out, gathers, 5);
     const double gps = gathers / (ms * 1e-3);
     printf(", \"%s\": {\"ms\": %.4f, \"Ggathers_per_s\": %.1f, \"per_sm_cycle\": %.3f}", names[v], ms, gps / 1e9, gps / (sms * (khz * 1e3)));
+  }
+
+  {
+    make_idx<<<sms * 8, 256>>>(idx, gathers, table, 1);
+    CHECK(cudaDeviceSynchronize());
+    cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = x; rd.res.linear.desc = cudaCreateChannelDesc<int2>();
+    rd.res.linear.sizeInBytes = sizeof(double) * table;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td)); td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) == cudaSuccess) {
+      const unsigned grid = (unsigned)(gathers / TILE);
+      cudaEvent_t e0, e1; CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+      for (int v = 0; v < 2; ++v) {
+        for (int r = 0; r < 2; ++r) { if (v == 0) k_tex<<<grid, THREADS>>>(idx, tex, out); else k_mix<<<grid, THREADS>>>(idx, x, tex, out); }
+        CHECK(cudaDeviceSynchronize());
+        CHECK(cudaEventRecord(e0));
+        for (int r = 0; r < 5; ++r) { if (v == 0) k_tex<<<grid, THREADS>>>(idx, tex, out); else k_mix<<<grid, THREADS>>>(idx, x, tex, out); }
+        CHECK(cudaEventRecord(e1)); CHECK(cudaEventSynchronize(e1));
+        float ms = 0; CHECK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 5;
+        const double gps = gathers / (ms * 1e-3);
+        printf(", \"%s\": {\"ms\": %.4f, \"Ggathers_per_s\": %.1f, \"per_sm_cycle\": %.3f}", v == 0 ? "tex_int2" : "ldg_tex_mix", ms, gps / 1e9, gps / (sms * (khz * 1e3)));
+      }
+    } else { cudaGetLastError(); printf(", \"tex_int2\": null"); }
+    // shared-memory window, 8 K / 16 K doubles (64 / 128 KB) per CTA; indices uniform over the window (random banks)
+    make_idx<<<sms * 8, 256>>>(idx, gathers, table, 0);
+    CHECK(cudaDeviceSynchronize());
+    for (int slice_k = 8; slice_k <= 16; slice_k *= 2) {
+      const int slice = slice_k << 10;
+      const size_t smem = sizeof(double) * slice;
+      CHECK(cudaFuncSetAttribute(k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      for (int tiles = 1; tiles <= 16; tiles *= 4) {
+        const int64_t per_cta = (int64_t)tiles * SM_THREADS * PER;
+        int64_t ctas = gathers / per_cta;
+        if ((int64_t)ctas * slice > table) ctas = table / slice;
+        cudaEvent_t e0, e1; CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+        k_smem<<<(unsigned)ctas, SM_THREADS, smem>>>(idx, x, out, slice, tiles);
+        CHECK(cudaDeviceSynchronize());
+        CHECK(cudaEventRecord(e0));
+        for (int r = 0; r < 5; ++r) k_smem<<<(unsigned)ctas, SM_THREADS, smem>>>(idx, x, out, slice, tiles);
+        CHECK(cudaEventRecord(e1)); CHECK(cudaEventSynchronize(e1));
+        float ms = 0; CHECK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 5;
+        const double g = (double)ctas * per_cta, gps = g / (ms * 1e-3);
+        printf(", \"smem%dk_t%d\": {\"ms\": %.4f, \"Ggathers_per_s\": %.1f, \"per_sm_cycle\": %.3f, \"fill_bytes_per_gather\": %.2f}", slice_k, tiles, ms, gps / 1e9,
+               gps / (sms * (khz * 1e3)), 8.0 * slice / per_cta);
+      }
+    }
   }
   printf("}\n");
   return 0;

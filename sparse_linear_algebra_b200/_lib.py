@@ -101,6 +101,7 @@ SIGNATURES = {
     "sla_cgne_step": (C.c_int, [_p, _p, _p]),
     "sla_krylov_get": (C.c_int, [_p, _p, C.c_int, _pf64]),
     "sla_krylov_view": (C.c_int, [_p, _p, C.c_int, _pp]),
+    "sla_krylov_clone": (C.c_int, [_p, _p, _pp]),
     "sla_krylov_free": (None, [_p]),
     "sla_solve_opts_default": (None, [_popts]),
     "sla_linsolve0": (C.c_int, [_p, C.c_int, _p, _p, _p, _popts, _p, _pint, _pf64]),

@@ -133,7 +133,7 @@ sla_status sla_vec_alloc(sla_ctx* c, int64_t n, sla_vec** out) {
   if (!c || !out || n < 0) return SLA_ERR_INVALID;
   sla_vec* v = new (std::nothrow) sla_vec();
   if (!v) return sla_fail(c, SLA_ERR_ALLOC, "vec alloc");
-  v->ctx = c; v->n = n; v->version = 1; v->owns = true; v->d = nullptr;
+  v->ctx = c; v->n = n; v->version = ++c->stamp; v->owns = true; v->d = nullptr;
   // round up so that 128-bit accesses of the last pair stay inside the allocation
   cudaError_t e = cudaMalloc(&v->d, sizeof(double) * (size_t)((n + 2) & ~(int64_t)1));
   if (e != cudaSuccess) { delete v; return sla_fail(c, SLA_ERR_ALLOC, "cudaMalloc failed for a vector"); }
@@ -151,7 +151,7 @@ extern "C" sla_status sla_vec_upload(sla_ctx* c, sla_vec* v, const double* x) {
   if (!c || !v || (!x && v->n > 0)) return SLA_ERR_INVALID;
   SLA_CUDA(c, cudaMemcpyAsync(v->d, x, sizeof(double) * (size_t)v->n, cudaMemcpyHostToDevice, c->stream));
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));   // the host buffer is only borrowed for the call
-  v->version++;
+  sla_touch(v);
   return SLA_OK;
 }
 
@@ -171,7 +171,7 @@ extern "C" sla_status sla_vec_copy(sla_ctx* c, const sla_vec* src, sla_vec* dst)
   if (!c || !src || !dst) return SLA_ERR_INVALID;
   if (src->n != dst->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "vec_copy: dimensions differ");
   SLA_CUDA(c, cudaMemcpyAsync(dst->d, src->d, sizeof(double) * (size_t)src->n, cudaMemcpyDeviceToDevice, c->stream));
-  dst->version++;
+  sla_touch(dst);
   return SLA_OK;
 }
 
@@ -183,7 +183,7 @@ extern "C" sla_status sla_vec_fill(sla_ctx* c, sla_vec* v, double a) {
   if (!c || !v) return SLA_ERR_INVALID;
   fill_kernel<<<SLA_NUM_SMS * 4, 256, 0, c->stream>>>(v->d, v->n, a);
   SLA_LAUNCH_CHECK(c);
-  v->version++;
+  sla_touch(v);
   return SLA_OK;
 }
 
@@ -214,7 +214,7 @@ extern "C" sla_status sla_spmv(sla_ctx* c, const sla_csr* A, const sla_vec* x, s
   if (A->m != y->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "matVec : output vector has the wrong dimension");
   if (x->d == y->d) return sla_fail(c, SLA_ERR_INVALID, "matVec : x and y must be distinct vectors");
   SLA_TRY(sla_spmv_launch(c, A, x->d, y->d, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
-  y->version++;
+  sla_touch(y);
   return SLA_OK;
 }
 
@@ -260,7 +260,7 @@ extern "C" sla_status sla_vec_add(sla_ctx* c, const sla_vec* x, const sla_vec* y
   SLA_TRY(check3(c, x, y, z, "^+^ : dimensions differ"));
   Ptrs<2> in{{x->d, y->d}}; Ptrs<1> o{{z->d}};
   SLA_TRY(ew_launch(c, OpAdd{}, x->n, in, o));
-  z->version++;
+  sla_touch(z);
   return SLA_OK;
 }
 
@@ -268,7 +268,7 @@ extern "C" sla_status sla_vec_sub(sla_ctx* c, const sla_vec* x, const sla_vec* y
   SLA_TRY(check3(c, x, y, z, "^-^ : dimensions differ"));
   Ptrs<2> in{{x->d, y->d}}; Ptrs<1> o{{z->d}};
   SLA_TRY(ew_launch(c, OpSub{}, x->n, in, o));
-  z->version++;
+  sla_touch(z);
   return SLA_OK;
 }
 
@@ -277,7 +277,7 @@ extern "C" sla_status sla_vec_scale(sla_ctx* c, double a, const sla_vec* x, sla_
   Ptrs<1> in{{x->d}}; Ptrs<1> o{{z->d}};
   OpScale op; op.a = a;
   SLA_TRY(ew_launch(c, op, x->n, in, o));
-  z->version++;
+  sla_touch(z);
   return SLA_OK;
 }
 
@@ -286,7 +286,7 @@ extern "C" sla_status sla_vec_axpy(sla_ctx* c, double a, const sla_vec* x, const
   Ptrs<2> in{{x->d, y->d}}; Ptrs<1> o{{z->d}};
   OpAxpy op; op.a = a;
   SLA_TRY(ew_launch(c, op, x->n, in, o));
-  z->version++;
+  sla_touch(z);
   return SLA_OK;
 }
 
@@ -298,7 +298,7 @@ extern "C" sla_status sla_vec_normalize2(sla_ctx* c, const sla_vec* x, sla_vec* 
   Ptrs<1> o{{z->d}};
   OpScaleDev op; op.slot = S_INVN; op.a = 0;
   SLA_TRY(ew_launch(c, op, x->n, in, o));
-  z->version++;
+  sla_touch(z);
   return SLA_OK;
 }
 

@@ -33,6 +33,7 @@ struct sla_ctx {
   unsigned int* counter;     // "last block" tickets, one per reduction site
   double* h_scal;            // pinned host mirror for scalar read-back
   int64_t launches;
+  uint64_t stamp;            // source of the vectors' write stamps: strictly increasing, so a stamp never repeats (krylov.cu rho cache)
   void* nccl;                // ncclComm_t when world > 1
   void* nccl_x;              // second communicator (ncclCommSplit) for the x exchange on comm_stream
   cudaStream_t comm_stream;  // the x exchange runs here so that it overlaps the column-panel kernels
@@ -55,7 +56,7 @@ struct sla_vec {
   sla_ctx* ctx;
   int64_t n;
   double* d;
-  uint64_t version;          // bumped on every write through the API (invalidates cached dots)
+  uint64_t version;          // stamp of the last write through the API, drawn from ctx->stamp (invalidates cached dots)
   bool owns;
 };
 
@@ -126,6 +127,9 @@ struct sla_krylov {
   const sla_vec* rho_r0hat;
   uint64_t rho_r0hat_version, rho_r_version;
 };
+
+// every write through the API re-stamps the vector with a value no vector of this context ever carried before
+static inline void sla_touch(sla_vec* v) { if (v) v->version = ++v->ctx->stamp; }
 
 static inline sla_status sla_fail(sla_ctx* c, sla_status s, const char* msg) {
   if (c) snprintf(c->err, sizeof(c->err), "%s", msg);

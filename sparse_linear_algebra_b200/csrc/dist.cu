@@ -112,8 +112,8 @@ void sla_dist_detach(sla_ctx* c) {
 // one-thread kernel: the scalar post-processing of a grid reduction, run after the all-reduce
 __global__ void finalize_kernel(int fin, int dst, double* scal, int src, int nv) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double sum[8];
-    for (int k = 0; k < nv && k < 8; ++k) sum[k] = scal[src + k];
+    double sum[32];
+    for (int k = 0; k < nv && k < 32; ++k) sum[k] = scal[src + k];
     finalize_scalars(fin, dst, scal, sum, nv);
   }
 }
@@ -122,7 +122,7 @@ __global__ void finalize_kernel(int fin, int dst, double* scal, int src, int nv)
 sla_status sla_dist_finish_reduction(sla_ctx* c, int nv, int fin, int dst) {
   if (c->world <= 1) return SLA_OK;
   // peer-memory path: all-reduce + post-processing in ONE single-CTA kernel (p2p.cu)
-  if (sla_p2p_active(c) && nv <= 8) return sla_p2p_allreduce(c, nv, fin == FIN_STORE ? dst : S_RAW, fin, dst);
+  if (sla_p2p_active(c) && nv <= 32) return sla_p2p_allreduce(c, nv, fin == FIN_STORE ? dst : S_RAW, fin, dst);
   ncclComm_t comm = (ncclComm_t)c->nccl;
   if (fin == FIN_STORE) {
     // raw sums were written straight to their destination slots

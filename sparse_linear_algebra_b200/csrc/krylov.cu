@@ -33,6 +33,24 @@ extern "C" void sla_krylov_free(sla_krylov* st) {
   delete st;
 }
 
+// A deep copy of the record (state AND work vectors are fresh allocations).  The reference's steps are pure:
+// `iterate (bicgstabStep aa r0hat) st0 !! 20` (README.md:208) keeps st0 alive, so a drop-in `step` is clone-then-advance
+// (hs/.../B200.hs); callers that own the record exclusively keep using the in-place step.
+extern "C" sla_status sla_krylov_clone(sla_ctx* c, const sla_krylov* st, sla_krylov** out) {
+  if (!c || !st || !out) return SLA_ERR_INVALID;
+  *out = nullptr;
+  sla_krylov* cp = nullptr;
+  SLA_TRY(krylov_alloc(c, st->kind, st->n, st->u != nullptr, &cp));
+  sla_status s = sla_vec_copy(c, st->x, cp->x);
+  if (s == SLA_OK) s = sla_vec_copy(c, st->r, cp->r);
+  if (s == SLA_OK) s = sla_vec_copy(c, st->p, cp->p);
+  if (s == SLA_OK && st->u) s = sla_vec_copy(c, st->u, cp->u);
+  if (s != SLA_OK) { sla_krylov_free(cp); return s; }
+  cp->rho_valid = false;              // rho = r <.> r0hat is recomputed by the clone's first step (the reference recomputes it every step)
+  *out = cp;
+  return SLA_OK;
+}
+
 static const sla_vec* krylov_field(const sla_krylov* st, int field) {
   switch (field) {
     case SLA_FIELD_X: return st->x;
@@ -82,7 +100,7 @@ static sla_status init_residual(sla_ctx* c, const sla_csr* A, const sla_vec* b, 
   return SLA_OK;
 }
 
-static void bump(sla_vec* v) { if (v) v->version++; }
+static void bump(sla_vec* v) { sla_touch(v); }
 
 // rho = r <.> rhat is carried on the device from the previous step while nobody touched r, rhat or the
 // scalar slots; otherwise it is recomputed (the reference recomputes it every step, Sparse.hs:974).
@@ -256,7 +274,7 @@ extern "C" sla_status sla_linsolve0(sla_ctx* c, int method, const sla_csr* A, co
   if (diag) {                                 // isDiagonalSM aa' = return $ reciprocal aa' #> b'   :1024-1025
     Ptrs<2> in{{A->val, b->d}}; Ptrs<1> out{{x->d}};
     SLA_TRY(ew_launch(c, OpDiagSolve{}, A->m, in, out));
-    x->version++;
+    sla_touch(x);
     return SLA_OK;
   }
   if (method != SLA_BICGSTAB_ && method != SLA_CGS_ && method != SLA_CGNE_) {   // IterE   :1031
@@ -314,74 +332,98 @@ extern "C" sla_status sla_linsolve0_host(sla_ctx* c, int method, const sla_csr* 
 }
 
 // ---- Arnoldi -------------------------------------------------------------------------------------------
+// One Arnoldi step = (#>) + three streaming kernels, all asynchronous: the Hessenberg column, the breakdown test and (for
+// GMRES) the Givens rotations stay on the device, so a whole cycle of kn steps is queued without a host round trip.
+//   tsmv_t_kernel   h_k = q_k <.> w for ALL k <= j in one launch (w read once; NC <= 32 columns per launch)
+//   lincomb_kernel  w <- w - sum_k h_k q_k (the reference's left-to-right association) + ||w||^2
+//   arn_finish_kernel  q_{j+1} = recip(||w||) .* w ; thread 0 files the column of H (and rotates it for GMRES)
+// Algorithmic bytes per step j: B_spmv + 16 n (j+1) + 32 n — Q is read twice, w is read by the dots,
+// read and written by the projection, read again by the scaling that writes q_{j+1}.
 
-#define TS_CH 8   // basis columns handled per pass of the tall-skinny kernels
+#define TS_NC 32   // basis columns per launch of the tall-skinny dot kernel
 
-// h[k0 + k] = q_{k0+k} <.> w   for k < nc <= TS_CH        (hhcoli = fmap (`dot` aqi) qv, Sparse.hs:655)
+// h[k0 + k] = q_{k0+k} <.> w   for k < nc <= NC        (hhcoli = fmap (`dot` aqi) qv, Sparse.hs:655)
+template <int NC>
 __global__ void __launch_bounds__(EW_THREADS)
 tsmv_t_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int k0, int nc, const double* __restrict__ w,
-              double* scal, double* partials, unsigned int* counter, int slot0) {
-  __shared__ double red[TS_CH * 32];
-  double acc[TS_CH];
+              double* scal, double* partials, unsigned int* counter, int fin, int slot0) {
+  __shared__ double red[NC * 32];
+  double acc[NC];
 #pragma unroll
-  for (int k = 0; k < TS_CH; ++k) acc[k] = 0.0;
+  for (int k = 0; k < NC; ++k) acc[k] = 0.0;
   const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double2* Q2 = reinterpret_cast<const double2*>(Q + (int64_t)k0 * ld);
+  const int64_t ld2 = ld >> 1;                        // ld is a multiple of 16 doubles
   for (int64_t i = gtid; i < n2; i += stride) {
     const double2 wv = reinterpret_cast<const double2*>(w)[i];
 #pragma unroll
-    for (int k = 0; k < TS_CH; ++k) {
-      if (k < nc) {
-        const double2 q = reinterpret_cast<const double2*>(Q + (int64_t)(k0 + k) * ld)[i];
-        acc[k] += q.x * wv.x;
-        acc[k] += q.y * wv.y;
+    for (int kb = 0; kb < NC; kb += 8) {
+      if (kb < nc) {                                  // warp-uniform
+        double2 q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (kb + k < nc) q[k] = Q2[(int64_t)(kb + k) * ld2 + i];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (kb + k < nc) { acc[kb + k] += q[k].x * wv.x; acc[kb + k] += q[k].y * wv.y; }
       }
     }
   }
   if ((n & 1) && gtid == 0) {
     for (int k = 0; k < nc; ++k) acc[k] += Q[(int64_t)(k0 + k) * ld + n - 1] * w[n - 1];
   }
-  block_sum<TS_CH>(acc, red);
-  grid_reduce_finish<TS_CH>(acc, partials, counter, scal, FIN_STORE, slot0 + k0, red);
+  block_sum<NC>(acc, red);
+  grid_reduce_finish<NC>(acc, partials, counter, scal, fin, slot0 + k0, red);
 }
 
-// out_i = base_i -/+ (((c_0 q_0i) + c_1 q_1i) + ... + c_{nc-1} q_{nc-1,i}), coefficients in scal[S_HCOL..];
+// out_i = base_i -/+ (((c_0 q_0i) + c_1 q_1i) + ... + c_{nc-1} q_{nc-1,i}), coefficients in scal[slot0..];
 // SIGN = -1: qipnn = aqi ^-^ foldl' (^+^) zv (zipWith (.*) hhcoli qv), plus sum of squares (Sparse.hs:657-659)
-// SIGN = +1: x = x ^+^ Q y (GMRES update)
+// SIGN = +1: x = x ^+^ Q y (GMRES update); nc_dev (optional) caps the column count with a device-side value
 template <int SIGN>
 __global__ void __launch_bounds__(EW_THREADS)
 lincomb_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int nc, const double* base, double* out,
-               double* scal, double* partials, unsigned int* counter, int fin, int slot0) {
+               double* scal, double* partials, unsigned int* counter, int fin, int slot0, const int* nc_dev) {
   __shared__ double coef[SLA_MAX_KRYLOV + 2];
   __shared__ double red[32];
+  if (nc_dev) { const int cap = *nc_dev; if (cap < nc) nc = cap; }
   for (int k = threadIdx.x; k < nc; k += blockDim.x) coef[k] = scal[slot0 + k];
   __syncthreads();
   double acc[1] = {0.0};
   const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t i = gtid; i < n2; i += stride) {
-    double2 s;
-    {
-      const double2 q = reinterpret_cast<const double2*>(Q)[i];
-      s.x = __dmul_rn(coef[0], q.x); s.y = __dmul_rn(coef[0], q.y);      // zeroSV ^+^ (h0 .* q0) = h0 .* q0
+  const double2* Q2 = reinterpret_cast<const double2*>(Q);
+  const int64_t ld2 = ld >> 1;
+  if (nc > 0) {
+    for (int64_t i = gtid; i < n2; i += stride) {
+      double2 s = make_double2(0.0, 0.0);
+      for (int kb = 0; kb < nc; kb += 8) {              // loads in batches of 8 columns, sums strictly in column order
+        double2 q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (kb + k < nc) q[k] = Q2[(int64_t)(kb + k) * ld2 + i];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (kb + k < nc) {
+            const double ck = coef[kb + k];
+            if (kb + k == 0) { s.x = __dmul_rn(ck, q[k].x); s.y = __dmul_rn(ck, q[k].y); }   // zeroSV ^+^ (h0 .* q0) = h0 .* q0
+            else { s.x = __dadd_rn(s.x, __dmul_rn(ck, q[k].x)); s.y = __dadd_rn(s.y, __dmul_rn(ck, q[k].y)); }
+          }
+        }
+      }
+      const double2 b = reinterpret_cast<const double2*>(base)[i];
+      double2 o;
+      o.x = SIGN < 0 ? __dsub_rn(b.x, s.x) : __dadd_rn(b.x, s.x);
+      o.y = SIGN < 0 ? __dsub_rn(b.y, s.y) : __dadd_rn(b.y, s.y);
+      reinterpret_cast<double2*>(out)[i] = o;
+      acc[0] += o.x * o.x + o.y * o.y;
     }
-    for (int k = 1; k < nc; ++k) {
-      const double2 q = reinterpret_cast<const double2*>(Q + (int64_t)k * ld)[i];
-      s.x = __dadd_rn(s.x, __dmul_rn(coef[k], q.x));
-      s.y = __dadd_rn(s.y, __dmul_rn(coef[k], q.y));
+    if ((n & 1) && gtid == 0) {
+      const int64_t i = n - 1;
+      double s = __dmul_rn(coef[0], Q[i]);
+      for (int k = 1; k < nc; ++k) s = __dadd_rn(s, __dmul_rn(coef[k], Q[(int64_t)k * ld + i]));
+      const double o = SIGN < 0 ? __dsub_rn(base[i], s) : __dadd_rn(base[i], s);
+      out[i] = o;
+      acc[0] += o * o;
     }
-    const double2 b = reinterpret_cast<const double2*>(base)[i];
-    double2 o;
-    o.x = SIGN < 0 ? __dsub_rn(b.x, s.x) : __dadd_rn(b.x, s.x);
-    o.y = SIGN < 0 ? __dsub_rn(b.y, s.y) : __dadd_rn(b.y, s.y);
-    reinterpret_cast<double2*>(out)[i] = o;
-    acc[0] += o.x * o.x + o.y * o.y;
-  }
-  if ((n & 1) && gtid == 0) {
-    const int64_t i = n - 1;
-    double s = __dmul_rn(coef[0], Q[i]);
-    for (int k = 1; k < nc; ++k) s = __dadd_rn(s, __dmul_rn(coef[k], Q[(int64_t)k * ld + i]));
-    const double o = SIGN < 0 ? __dsub_rn(base[i], s) : __dadd_rn(base[i], s);
-    out[i] = o;
-    acc[0] += o * o;
   }
   if (SIGN < 0) {
     block_sum<1>(acc, red);
@@ -389,11 +431,125 @@ lincomb_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int nc, cons
   }
 }
 
+// Device-resident bookkeeping of one Arnoldi run / GMRES cycle (one allocation).
+//   H   (kn+1) x kn column-major: the Hessenberg matrix (arnoldi) or the rotated upper-triangular factor (GMRES)
+//   cs, sn, g, y: Givens rotations, rotated right-hand side, solution of the least-squares problem (GMRES)
+//   meta[0] = first column count at which the run has to stop (-1: none), meta[1] = columns used by the last solve
+//   res[0] = |g_{j+1}| at the stop column (GMRES residual estimate)
+struct arn_dev {
+  double *H, *cs, *sn, *g, *y, *res;
+  int* meta;
+  int ldh;
+  void* block;
+};
+
+static sla_status arn_dev_alloc(sla_ctx* c, int kn, arn_dev* d) {
+  const size_t nd = (size_t)(kn + 1) * kn + 4 * (size_t)(kn + 2) + 2;
+  const size_t bytes = nd * sizeof(double) + 4 * sizeof(int);
+  memset(d, 0, sizeof(*d));
+  if (cudaMalloc(&d->block, bytes) != cudaSuccess) { cudaGetLastError(); return sla_fail(c, SLA_ERR_ALLOC, "cudaMalloc failed for the Hessenberg block"); }
+  SLA_CUDA(c, cudaMemsetAsync(d->block, 0, bytes, c->stream));
+  double* p = (double*)d->block;
+  d->ldh = kn + 1;
+  d->H = p; p += (size_t)(kn + 1) * kn;
+  d->cs = p; p += kn + 2; d->sn = p; p += kn + 2; d->g = p; p += kn + 2; d->y = p; p += kn + 2; d->res = p; p += 2;
+  d->meta = (int*)p;
+  return SLA_OK;
+}
+
+__global__ void arn_reset_kernel(int* meta, double* res) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { meta[0] = -1; meta[1] = 0; res[0] = 0.0; }
+}
+
+// q_{j+1} = (recip h_{j+1,j}) .* w, and thread 0 of CTA 0 files column j:
+//   GM = false (arnoldi): H[:, j] = (h_0 .. h_j, ||w||); breakdown = nearZero ||w|| for j > 0 (arnInit has no test)  Sparse.hs:643-666
+//   GM = true  (GMRES):   h = first-pass + re-orthogonalisation dots, previous rotations applied, new rotation formed,
+//                         g updated; the run stops at the first column whose residual estimate meets tol (or on breakdown)
+template <bool GM>
+__global__ void __launch_bounds__(EW_THREADS)
+arn_finish_kernel(const double* __restrict__ w, double* __restrict__ qnext, int64_t n, const double* __restrict__ scal, int j,
+                  int reorth, arn_dev d, double tol, double g0) {
+  const double a = scal[S_INVN];
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = gtid; i < n2; i += stride) {
+    const double2 v = reinterpret_cast<const double2*>(w)[i];
+    reinterpret_cast<double2*>(qnext)[i] = make_double2(__dmul_rn(a, v.x), __dmul_rn(a, v.y));
+  }
+  if (gtid == 0) {
+    if (n & 1) qnext[n - 1] = __dmul_rn(a, w[n - 1]);
+    double* hc = d.H + (size_t)j * d.ldh;
+    const double nrm = scal[S_NRM];
+    if (!GM) {
+      for (int k = 0; k <= j; ++k) hc[k] = scal[S_HCOL + k];
+      hc[j + 1] = nrm;
+      if (j > 0 && fabs(nrm) <= 1e-12 && d.meta[0] < 0) d.meta[0] = j + 1;
+    } else {
+      if (j == 0) d.g[0] = g0;
+      double prev = scal[S_HCOL] + (reorth ? scal[S_HCOL2] : 0.0);
+      for (int k = 0; k < j; ++k) {                      // apply the previous rotations to the new column
+        const double hn = scal[S_HCOL + k + 1] + (reorth ? scal[S_HCOL2 + k + 1] : 0.0);
+        hc[k] = d.cs[k] * prev + d.sn[k] * hn;
+        prev = -d.sn[k] * prev + d.cs[k] * hn;
+      }
+      const double bb = nrm, dd = hypot(prev, bb);
+      const double cj = dd == 0.0 ? 1.0 : prev / dd, sj = dd == 0.0 ? 0.0 : bb / dd;
+      d.cs[j] = cj; d.sn[j] = sj;
+      hc[j] = cj * prev + sj * bb;
+      const double gj = d.g[j];
+      d.g[j + 1] = -sj * gj; d.g[j] = cj * gj;
+      if (d.meta[0] < 0) {
+        const double r = fabs(d.g[j + 1]);
+        d.res[0] = r;
+        if (r <= tol || fabs(bb) <= 1e-12) d.meta[0] = j + 1;
+      }
+    }
+  }
+}
+
+// GMRES: back-substitution R y = g over the first jn columns (jn = the stop column, or jmax when the cycle ran to its end);
+// y goes to scal[S_HCOL ..] where lincomb_kernel<+1> reads it, jn to meta[1]
+__global__ void gmres_solve_kernel(arn_dev d, int jmax, double* scal) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int jn = d.meta[0] >= 0 && d.meta[0] < jmax ? d.meta[0] : jmax;
+  for (int k = jn - 1; k >= 0; --k) {
+    double t = d.g[k];
+    for (int l = k + 1; l < jn; ++l) t -= d.H[(size_t)l * d.ldh + k] * d.y[l];
+    d.y[k] = t / d.H[(size_t)k * d.ldh + k];
+  }
+  for (int k = 0; k < jn; ++k) scal[S_HCOL + k] = d.y[k];
+  d.meta[1] = jn;
+}
+
 static unsigned ts_blocks(int64_t n) {
   int64_t b = ((n >> 1) + EW_THREADS - 1) / EW_THREADS;
   if (b < 1) b = 1;
   if (b > EW_MAX_BLOCKS) b = EW_MAX_BLOCKS;
   return (unsigned)b;
+}
+
+// grid of the tall-skinny dot kernel: whole waves of resident CTAs (its 2 NC accumulator registers limit the occupancy)
+template <int NC>
+static unsigned tsmv_grid(int64_t n) {
+  static int per_sm = 0;
+  if (!per_sm) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsmv_t_kernel<NC>, EW_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+  }
+  const unsigned cap = (unsigned)(SLA_NUM_SMS * per_sm), want = ts_blocks(n);
+  return want < cap ? want : cap;
+}
+
+static sla_status tsmv_launch(sla_ctx* c, const sla_dense* Q, int nq, const double* w, int slot0) {
+  const int64_t n = Q->rows, ld = Q->ld;
+  for (int k0 = 0; k0 < nq; k0 += TS_NC) {
+    const int nc = nq - k0 < TS_NC ? nq - k0 : TS_NC;
+    const int fin = fin_for(c, FIN_STORE);
+    if (nc <= 8) tsmv_t_kernel<8><<<tsmv_grid<8>(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, fin, slot0);
+    else if (nc <= 16) tsmv_t_kernel<16><<<tsmv_grid<16>(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, fin, slot0);
+    else tsmv_t_kernel<32><<<tsmv_grid<32>(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, fin, slot0);
+    SLA_LAUNCH_CHECK(c);
+    SLA_TRY(sla_dist_finish_reduction(c, nc, FIN_STORE, slot0 + k0));
+  }
+  return SLA_OK;
 }
 
 static sla_status dense_alloc(sla_ctx* c, int64_t rows, int64_t cols, sla_dense** out) {
@@ -410,36 +566,24 @@ static sla_status dense_alloc(sla_ctx* c, int64_t rows, int64_t cols, sla_dense*
   return SLA_OK;
 }
 
-// One Arnoldi step on the device: given basis columns 0..j of Q, append column j+1 and produce column j of H.
+// One Arnoldi step, queued on the stream: given basis columns 0..j of Q, append column j+1 and file column j of H.
 //   aqi = aa #> q_j ; h_k = q_k <.> aqi (k <= j) ; w = aqi - sum_k h_k q_k ; h_{j+1} = norm2 w ; q_{j+1} = w ./ h_{j+1}
-// hcol (host, j + 2 doubles) receives the column.  reorth = false is the reference's single classical
-// Gram-Schmidt pass (Sparse.hs:655-659); reorth = true repeats the projection once (CGS2) — used by GMRES only,
-// because single-pass CGS loses orthogonality on clustered spectra.
-static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j, double* w, double* hcol, bool reorth) {
+// reorth = false is the reference's single classical Gram-Schmidt pass (Sparse.hs:655-659); reorth = true repeats the
+// projection once (CGS2) — used by GMRES only, because single-pass CGS loses orthogonality on clustered spectra.
+template <bool GM>
+static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j, double* w, bool reorth, const arn_dev& d, double tol, double g0) {
   const int64_t n = Q->rows, ld = Q->ld;
   SLA_TRY(sla_spmv_launch(c, A, Q->d + (int64_t)j * ld, w, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
   const int nq = j + 1;
   for (int pass = 0; pass < (reorth ? 2 : 1); ++pass) {
     const int slot0 = pass == 0 ? S_HCOL : S_HCOL2;
-    for (int k0 = 0; k0 < nq; k0 += TS_CH) {
-      const int nc = nq - k0 < TS_CH ? nq - k0 : TS_CH;
-      tsmv_t_kernel<<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, slot0);
-      SLA_LAUNCH_CHECK(c);
-      SLA_TRY(sla_dist_finish_reduction(c, nc, FIN_STORE, slot0 + k0));
-    }
-    lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, fin_for(c, FIN_NORM_INV), slot0);
+    SLA_TRY(tsmv_launch(c, Q, nq, w, slot0));
+    lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, fin_for(c, FIN_NORM_INV), slot0, nullptr);
     SLA_LAUNCH_CHECK(c);
     SLA_TRY(sla_dist_finish_reduction(c, 1, FIN_NORM_INV, 0));
   }
-  // q_{j+1} = (recip h_{j+1,j}) .* w
-  { Ptrs<1> in{{w}}; Ptrs<1> o{{Q->d + (int64_t)(j + 1) * ld}}; OpScaleDev op; op.slot = S_INVN; op.a = 0; SLA_TRY(ew_launch(c, op, n, in, o)); }
-  // read back the column: h_0..h_j from S_HCOL.. (+ the correction from S_HCOL2..), h_{j+1} = S_NRM
-  SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + S_HCOL, c->scal + S_HCOL, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
-  if (reorth) SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + S_HCOL2, c->scal + S_HCOL2, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
-  SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + S_NRM, c->scal + S_NRM, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  SLA_CUDA(c, cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < nq; ++k) hcol[k] = c->h_scal[S_HCOL + k] + (reorth ? c->h_scal[S_HCOL2 + k] : 0.0);
-  hcol[nq] = c->h_scal[S_NRM];
+  arn_finish_kernel<GM><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(w, Q->d + (int64_t)(j + 1) * ld, n, c->scal, j, reorth ? 1 : 0, d, tol, g0);
+  SLA_LAUNCH_CHECK(c);
   return SLA_OK;
 }
 
@@ -458,8 +602,12 @@ extern "C" sla_status sla_arnoldi(sla_ctx* c, const sla_csr* A, const sla_vec* b
   sla_dense* Q = nullptr;
   SLA_TRY(dense_alloc(c, n, kn + 1, &Q));
   sla_vec* w = nullptr;
+  arn_dev d;
   sla_status s = sla_vec_alloc(c, n, &w);
-  if (s != SLA_OK) { sla_dense_free(Q); return s; }
+  if (s == SLA_OK) s = arn_dev_alloc(c, kn, &d); else memset(&d, 0, sizeof(d));
+  if (s != SLA_OK) { sla_vec_free(w); sla_dense_free(Q); return s; }
+  arn_reset_kernel<<<1, 32, 0, c->stream>>>(d.meta, d.res);
+  c->launches++;
   // q0 = normalize2 b   :643
   {
     Ptrs<1> in{{b->d}}; Ptrs<0> o0{};
@@ -467,37 +615,39 @@ extern "C" sla_status sla_arnoldi(sla_ctx* c, const sla_csr* A, const sla_vec* b
     Ptrs<1> o{{Q->d}}; OpScaleDev op; op.slot = S_INVN; op.a = 0;
     if (s == SLA_OK) s = ew_launch(c, op, n, in, o);
   }
-  // arnInit is the j = 0 step; modifyUntil then applies the step and tests `i == kn || breakdown`   :639-651
-  for (int z = 0; z < (kn + 1) * kn; ++z) h_host[z] = 0.0;
-  int i = 0;          // columns of H produced so far
-  bool brk = false;
-  double hcol[SLA_MAX_KRYLOV + 2];
-  while (s == SLA_OK) {
-    s = arnoldi_step(c, A, Q, i, w->d, hcol, false);
-    if (s != SLA_OK) break;
-    for (int k = 0; k <= i + 1; ++k) h_host[(int64_t)i * (kn + 1) + k] = hcol[k];
-    brk = i > 0 && fabs(hcol[i + 1]) <= 1e-12;      // nearZero qipnorm (arnInit itself has no breakdown test)   :666
-    ++i;
-    if (i == kn || brk) break;
-  }
+  // arnInit is the j = 0 step; modifyUntil then applies the step and tests `i == kn || breakdown`   :639-651.
+  // All kn steps are queued without a host round trip; the breakdown column (if any) is found afterwards and the columns
+  // computed past it are discarded — the same (Q, H) the reference returns when it stops there.
+  for (int j = 0; j < kn && s == SLA_OK; ++j) s = arnoldi_step<false>(c, A, Q, j, w->d, false, d, 0.0, 0.0);
+  std::vector<double> hfull((size_t)(kn + 1) * kn, 0.0);
+  int meta[4] = {-1, 0, 0, 0};
+  if (s == SLA_OK && cudaMemcpyAsync(hfull.data(), d.H, sizeof(double) * hfull.size(), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) s = sla_fail(c, SLA_ERR_CUDA, "arnoldi: copy of H failed");
+  if (s == SLA_OK && cudaMemcpyAsync(meta, d.meta, sizeof(meta), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) s = sla_fail(c, SLA_ERR_CUDA, "arnoldi: copy of the breakdown flag failed");
+  if (s == SLA_OK) s = sla_sync(c);
   sla_vec_free(w);
-  if (s != SLA_OK) { sla_dense_free(Q); return s; }
-  // on breakdown the reference returns H as (nmax+1) x nmax with nmax = i; repack the leading block
-  if (i < kn) {
-    for (int col = 0; col < i; ++col)
-      for (int row = 0; row <= i; ++row) h_host[(int64_t)col * (i + 1) + row] = h_host[(int64_t)col * (kn + 1) + row];
-    Q->cols = i + 1;
-  }
+  cudaFree(d.block);
+  if (s != SLA_OK) { cudaGetLastError(); sla_dense_free(Q); return s; }
+  const bool brk = meta[0] >= 0 && meta[0] <= kn;
+  const int i = brk ? meta[0] : kn;          // columns of H produced before the run stops
+  // H is (i+1) x i column-major; on breakdown the reference returns the leading block with nmax = i
+  for (int col = 0; col < i; ++col)
+    for (int row = 0; row <= i; ++row) h_host[(int64_t)col * (i + 1) + row] = row <= col + 1 ? hfull[(size_t)col * (kn + 1) + row] : 0.0;
+  for (int64_t z = (int64_t)i * (i + 1); z < (int64_t)(kn + 1) * kn; ++z) h_host[z] = 0.0;
+  if (i < kn) Q->cols = i + 1;
   *nmax_out = i;
   *Qout = Q;
   return brk ? SLA_ERR_BREAKDOWN : SLA_OK;
 }
 
 // ---- GMRES(restart) --------------------------------------------------------------------------------------
-// Restarted GMRES on the Arnoldi kernels above: classical Gram-Schmidt basis, Givens rotations on the host
-// for the (restart+1) x restart least-squares problem, x += Q y on the device.  The reference's own gmres
-// (arnoldi -> qr -> triUpperSolve -> Q y) is commented out (Sparse.hs:837-848); tolerance and iteration-cap
-// conventions follow linSolve0 (Sparse.hs:1034-1037).
+// Restarted GMRES on the Arnoldi kernels above: Gram-Schmidt basis with one re-orthogonalisation pass, Givens rotations
+// and the back-substitution of the (restart+1) x restart least-squares problem on the device (arn_finish_kernel<true>,
+// gmres_solve_kernel), x += Q y on the device; the host synchronises twice per CYCLE (restart residual, columns used),
+// never per step.  A cycle is queued to its end; when the residual estimate meets the tolerance at column j the later
+// columns of that (last) cycle are computed but not used.  The reference's own gmres (arnoldi -> qr -> triUpperSolve ->
+// Q y) is commented out (Sparse.hs:837-848); tolerance and iteration-cap conventions follow linSolve0 (Sparse.hs:1034-1037).
+// opts->check_every < 0: no stopping test (every cycle runs `restart` steps until max_iters; breakdown still stops a cycle)
+// — the fixed-work form "GMRES(30), 10 restarts" of BASELINE.json config 4.
 extern "C" sla_status sla_gmres(sla_ctx* c, const sla_csr* A, const sla_vec* b, const sla_vec* x0, int restart,
                                 const sla_solve_opts* opts_in, sla_vec* x, int* iters, double* resnorm) {
   if (!c || !A || !b || !x0 || !x) return SLA_ERR_INVALID;
@@ -507,15 +657,17 @@ extern "C" sla_status sla_gmres(sla_ctx* c, const sla_csr* A, const sla_vec* b, 
   sla_solve_opts_default(&o);
   if (opts_in) o = *opts_in;
   if (o.max_iters <= 0) o.max_iters = 200;
+  const bool never_stop = o.check_every < 0;
   const int64_t n = A->m;
   const int m = restart;
   sla_dense* Q = nullptr;
   sla_vec* w = nullptr;
+  arn_dev d;
+  memset(&d, 0, sizeof(d));
   SLA_TRY(dense_alloc(c, n, m + 1, &Q));
   sla_status s = sla_vec_alloc(c, n, &w);
+  if (s == SLA_OK) s = arn_dev_alloc(c, m, &d);
   if (s == SLA_OK && x != x0) s = sla_vec_copy(c, x0, x);
-  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), y(m, 0.0);
-  double hcol[SLA_MAX_KRYLOV + 2];
   int total = 0;
   double res = 0, tol = 0;
   bool first = true, done = false;
@@ -531,54 +683,36 @@ extern "C" sla_status sla_gmres(sla_ctx* c, const sla_csr* A, const sla_vec* b, 
     s = sla_read_scalars(c, S_NRM, 1, &beta);
     if (s != SLA_OK) break;
     res = beta;
-    if (first) { tol = o.tol_abs > o.tol_rel * beta ? o.tol_abs : o.tol_rel * beta; first = false; }
+    if (first) { tol = never_stop ? -1.0 : (o.tol_abs > o.tol_rel * beta ? o.tol_abs : o.tol_rel * beta); first = false; }
     if (!(beta > tol) || total >= o.max_iters) break;     // converged on the true residual (or NaN / cap)
-    for (int k = 0; k <= m; ++k) g[k] = 0.0;
-    g[0] = beta;
-    int j = 0;
-    for (; j < m && total < o.max_iters; ++j) {
-      s = arnoldi_step(c, A, Q, j, w->d, hcol, true);
-      if (s != SLA_OK) break;
-      ++total;
-      for (int k = 0; k < j; ++k) {                        // apply the previous rotations to the new column
-        const double t = cs[k] * hcol[k] + sn[k] * hcol[k + 1];
-        hcol[k + 1] = -sn[k] * hcol[k] + cs[k] * hcol[k + 1];
-        hcol[k] = t;
-      }
-      const double a = hcol[j], bb = hcol[j + 1], d = hypot(a, bb);
-      cs[j] = d == 0.0 ? 1.0 : a / d; sn[j] = d == 0.0 ? 0.0 : bb / d;
-      hcol[j] = cs[j] * a + sn[j] * bb; hcol[j + 1] = 0.0;
-      g[j + 1] = -sn[j] * g[j]; g[j] = cs[j] * g[j];
-      for (int k = 0; k <= j; ++k) H[(size_t)j * (m + 1) + k] = hcol[k];
-      res = fabs(g[j + 1]);
-      if (res <= tol || fabs(bb) <= 1e-12) { ++j; break; }
-    }
+    const int jmax = m < o.max_iters - total ? m : o.max_iters - total;
+    arn_reset_kernel<<<1, 32, 0, c->stream>>>(d.meta, d.res);
+    c->launches++;
+    for (int j = 0; j < jmax && s == SLA_OK; ++j) s = arnoldi_step<true>(c, A, Q, j, w->d, true, d, tol, beta);
     if (s != SLA_OK) break;
-    // back-substitution R y = g, then x = x + Q[:, 0..j-1] y
-    for (int k = j - 1; k >= 0; --k) {
-      double t = g[k];
-      for (int l = k + 1; l < j; ++l) t -= H[(size_t)l * (m + 1) + k] * y[l];
-      y[k] = t / H[(size_t)k * (m + 1) + k];
+    // R y = g on the device, then x = x + Q[:, 0..jn-1] y
+    gmres_solve_kernel<<<1, 32, 0, c->stream>>>(d, jmax, c->scal);
+    lincomb_kernel<1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, Q->ld, n, jmax, x->d, x->d, c->scal, c->partials, c->counter, FIN_STORE, S_HCOL, d.meta + 1);
+    c->launches += 2;
+    int meta[2] = {-1, 0};
+    double rest = 0;
+    if (cudaMemcpyAsync(meta, d.meta, sizeof(meta), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(&rest, d.res, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      s = sla_fail(c, SLA_ERR_CUDA, "gmres: CUDA error in the solution update");
+      break;
     }
-    if (j > 0) {
-      for (int k = 0; k < j; ++k) c->h_scal[S_HCOL + k] = y[k];
-      cudaMemcpyAsync(c->scal + S_HCOL, c->h_scal + S_HCOL, sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, c->stream);
-      lincomb_kernel<1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, Q->ld, n, j, x->d, x->d, c->scal, c->partials, c->counter, FIN_STORE, S_HCOL);
-      c->launches++;
-      if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-        s = sla_fail(c, SLA_ERR_CUDA, "gmres: CUDA error in the solution update");
-        break;
-      }
-    }
+    total += meta[1];
+    res = rest;
     if (total >= o.max_iters) {
       // report the true residual of the returned iterate
       s = residual_norm(c, A, x, b, &res);
       done = true;
     }
   }
-  x->version++;
+  sla_touch(x);
   if (iters) *iters = total;
   if (resnorm) *resnorm = res;
-  sla_vec_free(w); sla_dense_free(Q);
+  sla_vec_free(w); sla_dense_free(Q); cudaFree(d.block);
   return s;
 }

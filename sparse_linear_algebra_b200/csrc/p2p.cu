@@ -31,7 +31,9 @@
 #include <new>
 
 #define P2P_FLAG_BYTES 256                       // flags live in the first 256 bytes of a window
-#define P2P_AR_WINDOW_BYTES 4096                 // [2][W] u64 flags | [2][W][8] doubles
+#define P2P_MAX_NV 32                            // doubles per all-reduce (one Hessenberg column chunk of the Arnoldi dots)
+#define P2P_AR_THREADS 128
+#define P2P_AR_WINDOW_BYTES (P2P_FLAG_BYTES + 2 * SLA_MAX_WORLD * P2P_MAX_NV * 8)   // [2][W] u64 flags | [2][W][P2P_MAX_NV] doubles
 #define P2P_ITEM_LEN 4096                        // doubles per push work item (one CTA)
 #define P2P_PUSH_THREADS 256
 #define P2P_TIMEOUT_CYCLES 60000000000LL         // ~30 s at 1.9 GHz
@@ -90,32 +92,35 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned 
 }
 
 // ---- all-reduce + scalar post-processing -------------------------------------------------------------------
-// window: flags[b][r] at byte 8 * (b * SLA_MAX_WORLD + r), values[b][r][k] at byte 256 + 8 * ((b * SLA_MAX_WORLD + r) * 8 + k)
-__global__ void __launch_bounds__(32)
+// window: flags[b][r] at byte 8 * (b * SLA_MAX_WORLD + r), values[b][r][k] at byte 256 + 8 * ((b * SLA_MAX_WORLD + r) * P2P_MAX_NV + k)
+__global__ void __launch_bounds__(P2P_AR_THREADS)
 p2p_allreduce_kernel(char* const* __restrict__ peer, int rank, int world, unsigned long long seq, int nv, int src,
                      int fin, int dst, double* scal, int* err) {
+  __shared__ double sum[P2P_MAX_NV];
   const int t = threadIdx.x;
   const int b = (int)(seq & 1ull);
   const int slot = b * SLA_MAX_WORLD + rank;
-  if (t < world) {
-    char* w = peer[t];
-    double* vals = reinterpret_cast<double*>(w + P2P_FLAG_BYTES) + (size_t)slot * 8;
-    for (int k = 0; k < nv; ++k) st_relaxed_sys_f64(vals + k, scal[src + k]);
-    __threadfence_system();
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(w) + slot, seq);
+  for (int q = t; q < world * nv; q += P2P_AR_THREADS) {          // (peer, value) pairs
+    const int p = q / nv, k = q - p * nv;
+    st_relaxed_sys_f64(reinterpret_cast<double*>(peer[p] + P2P_FLAG_BYTES) + (size_t)slot * P2P_MAX_NV + k, scal[src + k]);
   }
-  __syncwarp();
+  __threadfence_system();
+  __syncthreads();
   char* mine = peer[rank];
-  if (t < world) wait_flag(reinterpret_cast<const unsigned long long*>(mine) + b * SLA_MAX_WORLD + t, seq, err);
-  __syncwarp();
-  if (t == 0) {
-    double sum[8];
-    for (int k = 0; k < 8; ++k) sum[k] = 0.0;
-    const double* vals = reinterpret_cast<const double*>(mine + P2P_FLAG_BYTES) + (size_t)b * SLA_MAX_WORLD * 8;
-    for (int r = 0; r < world; ++r)                    // rank order: the same bits on every rank
-      for (int k = 0; k < nv; ++k) sum[k] += ld_relaxed_sys_f64(vals + (size_t)r * 8 + k);
-    finalize_scalars(fin, dst, scal, sum, nv);
+  if (t < world) {
+    __threadfence_system();                                       // cumulative over the CTA's stores observed through the barrier
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(peer[t]) + slot, seq);
+    wait_flag(reinterpret_cast<const unsigned long long*>(mine) + b * SLA_MAX_WORLD + t, seq, err);
   }
+  __syncthreads();
+  if (t < nv) {
+    const double* vals = reinterpret_cast<const double*>(mine + P2P_FLAG_BYTES) + (size_t)b * SLA_MAX_WORLD * P2P_MAX_NV;
+    double a = 0.0;
+    for (int r = 0; r < world; ++r) a += ld_relaxed_sys_f64(vals + (size_t)r * P2P_MAX_NV + t);   // rank order: the same bits on every rank
+    sum[t] = a;
+  }
+  __syncthreads();
+  if (t == 0) finalize_scalars(fin, dst, scal, sum, nv);
 }
 
 // ---- x exchange ------------------------------------------------------------------------------------------
@@ -241,11 +246,11 @@ extern "C" int sla_p2p_enabled(const sla_ctx* c) { return c && c->p2p && c->p2p-
 
 bool sla_p2p_active(const sla_ctx* c) { return c->p2p && c->p2p->enabled; }
 
-// all-reduce of scal[src .. src+nv) over the ranks followed by the scalar post-processing `fin` (nv <= 8)
+// all-reduce of scal[src .. src+nv) over the ranks followed by the scalar post-processing `fin` (nv <= P2P_MAX_NV = 32)
 sla_status sla_p2p_allreduce(sla_ctx* c, int nv, int src, int fin, int dst) {
   sla_p2p* P = c->p2p;
   P->seq++;
-  p2p_allreduce_kernel<<<1, 32, 0, c->stream>>>(P->d_peer, c->rank, c->world, P->seq, nv, src, fin, dst, c->scal, P->d_err);
+  p2p_allreduce_kernel<<<1, P2P_AR_THREADS, 0, c->stream>>>(P->d_peer, c->rank, c->world, P->seq, nv, src, fin, dst, c->scal, P->d_err);
   SLA_LAUNCH_CHECK(c);
   return SLA_OK;
 }

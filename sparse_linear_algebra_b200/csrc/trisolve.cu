@@ -583,7 +583,7 @@ sla_status tri_solve(sla_ctx* c, const sla_csr* A_, const sla_vec* b, sla_vec* x
     tri_solve_kernel<false><<<grid, TRI_SOLVE_THREADS, 0, c->stream>>>(A->row_ptr, A->col, A->val, A->tri_diag, P->order, b->d, A->tri_w,
                                                                        x->d, n, A->tri_ticket, backoff);
   SLA_LAUNCH_CHECK(c);
-  x->version++;
+  sla_touch(x);
   return SLA_OK;
 }
 

@@ -509,6 +509,12 @@ class KrylovState:
             self.ctx.lib.sla_krylov_free(self.h)
             self.h = None
 
+    def clone(self):
+        """Deep copy of the record: what a pure `step` (the reference's signature) advances instead of its argument."""
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.sla_krylov_clone(self.ctx.h, self.h, C.byref(h)))
+        return KrylovState(self.ctx, h, self.kind)
+
     def _field(self, f):
         v = C.c_void_p()
         self.ctx.check(self.ctx.lib.sla_krylov_view(self.ctx.h, self.h, f, C.byref(v)))
@@ -533,7 +539,11 @@ def bicgsInit(aa, b, x0):
     return _init("sla_bicgstab_init", BICGSTAB_, aa, b, x0)
 
 
-def bicgstabStep(aa, r0hat, st):
+def bicgstabStep(aa, r0hat, st, pure=False):
+    """bicgstabStep aa r0hat st (Sparse.hs:970-981).  pure=True is the reference's signature (st stays valid, a new record is
+    returned: `iterate (bicgstabStep aa r0hat) st0 !! 20`, README.md:208); the default advances st in place."""
+    if pure:
+        st = st.clone()
     aa.ctx.check(aa.ctx.lib.sla_bicgstab_step(aa.ctx.h, aa.h, r0hat.h, st.h))
     return st
 
@@ -542,7 +552,9 @@ def cgsInit(aa, b, x0):
     return _init("sla_cgs_init", CGS_, aa, b, x0)
 
 
-def cgsStep(aa, rhat, st):
+def cgsStep(aa, rhat, st, pure=False):
+    if pure:
+        st = st.clone()
     aa.ctx.check(aa.ctx.lib.sla_cgs_step(aa.ctx.h, aa.h, rhat.h, st.h))
     return st
 
@@ -551,7 +563,9 @@ def cgneInit(aa, b, x0):
     return _init("sla_cgne_init", CGNE_, aa, b, x0)
 
 
-def cgneStep(aa, st):
+def cgneStep(aa, st, pure=False):
+    if pure:
+        st = st.clone()
     aa.ctx.check(aa.ctx.lib.sla_cgne_step(aa.ctx.h, aa.h, st.h))
     return st
 
@@ -605,10 +619,12 @@ def arnoldi(aa, b, kn):
     return DenseBlock(ctx, q), H, st == L.SLA_ERR_BREAKDOWN
 
 
-def gmres(aa, b, x0, restart=30, nits=0, tol_abs=0.0, tol_rel=0.0, info=False):
+def gmres(aa, b, x0, restart=30, nits=0, tol_abs=0.0, tol_rel=0.0, info=False, fixed_work=False):
+    """Restarted GMRES(restart).  fixed_work=True runs exactly `nits` Arnoldi steps (no stopping test; BASELINE config 4's
+    "GMRES(30), 10 restarts" is restart=30, nits=300)."""
     ctx = aa.ctx
     x = SpVector.zeroSV(x0.dim, ctx)
-    o = _opts(nits, tol_abs, tol_rel, True, 1)
+    o = _opts(nits, tol_abs, tol_rel, True, -1 if fixed_work else 1)
     iters, res = C.c_int(0), C.c_double(0)
     ctx.check(ctx.lib.sla_gmres(ctx.h, aa.h, b.h, x0.h, restart, C.byref(o), x.h, C.byref(iters), C.byref(res)))
     return (x, iters.value, res.value) if info else x
