@@ -37,18 +37,34 @@ def load_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
+def kernel_source_stamp():
+    """sha256[:16] of the (#>) kernel source: profiles/traffic.json is only quoted while it was measured on this source."""
+    import hashlib
+
+    try:
+        with open(os.path.join(ROOT, "sparse_linear_algebra_b200", "csrc", "spmv.cu"), "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()[:16]
+    except Exception:
+        return None
+
+
 def load_traffic():
     """DRAM bytes of the cfg-2 (#>) from the committed ncu --set full capture (profiles/traffic.json): the step is TWO
     launches of spmv_tile_kernel (one per column panel), so the per-step figure — the one comparable with
-    `algorithmic_bytes_per_step` — is the sum over both.  Returns (per_step, per_launch, launches) or Nones."""
+    `algorithmic_bytes_per_step` — is the sum over both.  The file carries the stamp of the kernel source it was captured
+    on (`spmv_cu_sha16`); a capture of another source is stale and is NOT quoted.  Returns (per_step, per_launch, launches,
+    note)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             d = json.load(f)
-        per_launch = d.get("spmv_cfg2_dram_bytes_per_launch")
         launches = d.get("spmv_cfg2_launches_per_step", 2)
-        return d.get("spmv_cfg2_dram_bytes_per_step", per_launch * launches if per_launch else None), per_launch, launches
+        if d.get("spmv_cu_sha16") != kernel_source_stamp():
+            return None, None, launches, "profiles/traffic.json was captured on another version of csrc/spmv.cu: stale, not quoted"
+        per_launch = d.get("spmv_cfg2_dram_bytes_per_launch")
+        return (d.get("spmv_cfg2_dram_bytes_per_step", per_launch * launches if per_launch else None), per_launch, launches,
+                f"ncu --set full capture of this kernel source ({d.get('captured', 'undated')})")
     except Exception:
-        return None, None, None
+        return None, None, None, "no capture"
 
 
 class ClockSampler:
@@ -98,12 +114,24 @@ def spmv_bytes(n, nnz):
     return 12 * nnz + 20 * n + 4
 
 
-def cpu_baseline(threads, n_sample=2_000_000, reps=3):
+def host_sample_rows():
+    """Rows of the config-2 matrix the CPU legs run on: the full 10M when the host has the memory for the oracle's
+    containers (~6 GB, built in ~25 s), else a 2M-row sample of the same family."""
+    try:
+        with open("/proc/meminfo") as f:
+            avail_kb = next(int(line.split()[1]) for line in f if line.startswith("MemAvailable"))
+        return N_CFG2 if avail_kb >= 24 * 1024 * 1024 else 2_000_000
+    except Exception:
+        return 2_000_000
+
+
+def cpu_baseline(threads, n_sample=None, reps=3):
     """The oracle's (#>) (per-row ordered intersection + left fold, the reference's algorithm) timed on the
-    host cores on a bounded sample of config 2: same family, n_sample rows x 32 nnz/row."""
+    host cores on config 2 itself when the host memory allows (else a bounded sample of the same family)."""
     from oracle import oracle as ora
 
     ora.build()
+    n_sample = n_sample or host_sample_rows()
     A = ora.SpMatrix.synth(ora.GEN_UNIFORM, n_sample, K_CFG2, SEED_CFG2)
     x = ora.SpVector.synth(SEED_CFG2 + 1, n_sample)
     ora.time_matvec(A, x, 1, threads)
@@ -147,7 +175,7 @@ def run_reference(args):
 
     ora.build()
     threads = os.cpu_count() or 1
-    n_sample = 2_000_000
+    n_sample = host_sample_rows()
     A = ora.SpMatrix.synth(ora.GEN_UNIFORM, n_sample, K_CFG2, SEED_CFG2)
     x = ora.SpVector.synth(SEED_CFG2 + 1, n_sample)
     for _ in range(args.warmup):
@@ -157,17 +185,76 @@ def run_reference(args):
         ora.time_matvec(A, x, 1, threads)
     sec = (time.perf_counter() - t0) / args.steps
     gbs = spmv_bytes(n_sample, n_sample * K_CFG2) / sec / 1e9
-    sample = f"config-2 family (uniform, 32 nnz/row) at n={n_sample} rows per step; GB/s is size-normalised"
+    sample = (f"config 2 itself: n={n_sample} rows, {n_sample * K_CFG2} nnz per step" if n_sample == N_CFG2 else
+              f"config-2 family (uniform, 32 nnz/row) at n={n_sample} rows per step; GB/s is size-normalised")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: CSR SpMV (#>) fp64, 10M x 10M, 32 nnz/row, uniform columns (bounded sample)",
-                   "sample_rows": n_sample, "nnz_per_row": K_CFG2},
+        "config": {"workload": "cfg2: CSR SpMV (#>) fp64, 10M x 10M, 32 nnz/row, uniform columns" + ("" if n_sample == N_CFG2 else " (bounded sample)"),
+                   "n": n_sample, "nnz": n_sample * K_CFG2, "sample_rows": n_sample, "nnz_per_row": K_CFG2,
+                   "algorithmic_bytes_per_step": spmv_bytes(n_sample, n_sample * K_CFG2)},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def _seq_row_dot(cols, vals, xh):
+    """The reference's row product: strict left fold from 0 over ascending columns, products rounded once (Common.hs:259-260)."""
+    acc = 0.0
+    for cj, v in zip(cols.tolist(), vals.tolist()):
+        acc = acc + v * xh[cj]
+    return acc
+
+
+def parity_rows(y_local, row0, nloc, n, k, seed, kind, band, xh, exact, nrows=304):
+    """Checks `nrows` rows of this rank's slice of y = A x against rows regenerated by the oracle's generator
+    (oracle.synth_row) and folded the reference's way.  exact=True: the bits must match; else the SURVEY.md section 8(d) bound
+    |dy| <= (k_i + 2) u sum |a_ij x_j| (arrival-order exchange: same products, rotated fold).  Outside every timed region."""
+    from oracle import oracle as ora
+
+    rng = np.random.default_rng(1234 + row0)
+    rows = np.unique(np.concatenate([[0, 1, max(nloc - 1, 0), max(nloc - 2, 0)], rng.integers(0, max(nloc, 1), nrows - 4)]))
+    bit_exact, worst, bad = 0, 0.0, 0
+    for rl in rows.tolist():
+        if rl >= nloc:
+            continue
+        cols, vals = ora.synth_row(kind, n, k, seed, band, row0 + rl)
+        ref = _seq_row_dot(cols, vals, xh)
+        got = float(y_local[rl])
+        if got == ref:
+            bit_exact += 1
+            continue
+        bound = (len(cols) + 2) * 2.0 ** -53 * float(np.sum(np.abs(vals) * np.abs(xh[cols])))
+        ratio = abs(got - ref) / bound if bound > 0 else float("inf")
+        worst = max(worst, ratio)
+        if exact or ratio > 1.0:
+            bad += 1
+    return {"rows": int(len(rows)), "bit_exact_rows": bit_exact, "max_err_over_bound": worst, "bad_rows": bad}
+
+
+def parity_cfg2(A, y, starts, rank, world, dist, n, k):
+    """Parity of THIS run's cfg-2 result, outside the timed region: sampled rows of every rank's slice of y against rows
+    regenerated by the oracle (the checker; nothing of the timed path touches it)."""
+    from oracle import oracle as ora
+
+    ora.build()
+    nloc = starts[rank + 1] - starts[rank]
+    xh_full = np.asarray(ora.SpVector.synth(SEED_CFG2 + 1, n).toDenseListSV())
+    p2p_mode = getattr(A, "dist_p2p_mode", 0)
+    mine = parity_rows(y.toDenseListSV(), starts[rank], nloc, n, k, SEED_CFG2, ora.GEN_UNIFORM, 0, xh_full, exact=(p2p_mode != 2))
+    del xh_full
+    if dist is not None:
+        allp = [None] * world
+        dist.all_gather_object(allp, mine)
+    else:
+        allp = [mine]
+    return {"what": "rows of y = A x (cfg 2, this run) vs oracle.synth_row folded left to right",
+            "rows": sum(q["rows"] for q in allp), "bit_exact_rows": sum(q["bit_exact_rows"] for q in allp),
+            "max_err_over_bound": max(q["max_err_over_bound"] for q in allp),
+            "criterion": "bit-exact" if p2p_mode != 2 else "(k+2) u sum|a_ij x_j| (arrival-order exchange folds each row in rotated column order)",
+            "ok": all(q["bad_rows"] == 0 for q in allp)}
 
 
 def run_gpu(args):
@@ -245,6 +332,28 @@ def run_gpu(args):
     value = nbytes / (ms_per_step * 1e-3) / 1e9
     kernel_gbs = value / world                             # per-GPU share of the algorithmic bytes
 
+    # ---- per-step spread (each step individually synchronised; the headline is the back-to-back loop above)
+    each = []
+    for _ in range(min(args.steps, 20)):
+        barrier()
+        ctx.timer_start()
+        A.matVec(x, out=y)
+        each.append(max_over_ranks(ctx.timer_stop()))
+    step_stats = {"min": float(np.min(each)), "median": float(np.median(each)), "max": float(np.max(each)), "n": len(each),
+                  "note": "steps timed one by one with a synchronisation (and at N > 1 a barrier) between them"}
+
+    parity = parity_cfg2(A, y, starts, rank, world, dist, n, k)
+
+    # ---- what the exchange costs: the same kernels WITHOUT the x exchange (diagnostic switch, results invalid)
+    xch = None
+    if world > 1:
+        ctx.set_option("skip_exchange", 1)
+        ms_kernels, _ = timed(lambda: A.matVec(x, out=y), max(10, args.steps // 2), 3)
+        ctx.set_option("skip_exchange", 0)
+        A.matVec(x, out=y)
+        xch = {"step_ms": ms_per_step, "kernels_only_ms": ms_kernels, "exposed_exchange_ms": ms_per_step - ms_kernels,
+               "mode": getattr(A, "dist_p2p_mode", 0)}
+
     # ---- e2e: host buffers through sla_spmv_host (pinned x slice -> device, exchange + kernel, y slice -> host)
     import ctypes as C
 
@@ -274,7 +383,9 @@ def run_gpu(args):
     if world > 1:
         extra["collectives"] = {"allreduce": "peer-memory kernel over NVLink (csrc/p2p.cu)" if getattr(ctx, "p2p", False) else "nccl",
                                 "x_exchange": {1: "peer-memory push kernel (csrc/p2p.cu)",
-                                               2: "copy-engine all-gather consumed in arrival order (csrc/p2p.cu mode 2)"}.get(
+                                               2: "copy-engine all-gather consumed in arrival order (csrc/p2p.cu mode 2)",
+                                               3: "LL halo kernel (csrc/p2p.cu mode 3)",
+                                               4: "copy-engine all-gather waited for as a whole (csrc/p2p.cu mode 4)"}.get(
                                     getattr(A, "dist_p2p_mode", 0), "ncclAllGather" if getattr(A, "dist_allgather", False) else "nccl send/recv")}
 
     def sptrsv_extra(tag, M, rhs):
@@ -331,8 +442,45 @@ def run_gpu(args):
         extra["bicgstab_cfg3_ms_per_iter"] = ms3
         extra["bicgstab_cfg3_gbs"] = b3 / (ms3 * 1e-3) / 1e9
         extra["bicgstab_cfg3_launches_per_iter"] = l3 / its
+        # parity of this run: after its+5 steps the recurrence residual still equals the true residual b - A x (size-independent
+        # property: it exercises the distributed (#>), both fused dots and the all-reduced scalars of every step)
+        r0n = rhat.norm2()
+        true_res = ((L3 @ st.x) - b).norm2()
+        rec_res = st.r.norm2()
+        extra["bicgstab_cfg3_parity"] = {"steps": its + 5, "true_residual": true_res, "recurrence_residual": rec_res, "r0": r0n,
+                                         "ok": bool(abs(true_res - rec_res) <= 1e-8 * r0n and np.isfinite(true_res))}
         ms3s, _ = timed(lambda: L3.matVec(xt, out=b), its, 3)
         extra["spmv_cfg3_gbs"] = spmv_bytes(n3, nnz3) / (ms3s * 1e-3) / 1e9
+        if world > 1:
+            ctx.set_option("skip_exchange", 1)
+            ms3k, _ = timed(lambda: L3.matVec(xt, out=b), its, 3)
+            ctx.set_option("skip_exchange", 0)
+            extra["spmv_cfg3_exchange"] = {"step_ms": ms3s, "kernels_only_ms": ms3k, "exposed_exchange_ms": ms3s - ms3k,
+                                           "mode": getattr(L3, "dist_p2p_mode", 0)}
+            # a 256^2 Laplacian through the same distributed code path against the oracle's trajectory (5 steps)
+            from oracle import oracle as ora
+
+            gs = 256
+            Ls = gen(sla.GEN_LAPLACE2D, gs * gs, 5, 0, gs)
+            ss = Ls.row_starts
+            xs = vec(gs * gs, 3, ss)
+            bs = Ls @ xs
+            sts = sla.bicgsInit(Ls, bs, sla.SpVector.zeroSV(ss[rank + 1] - ss[rank]))
+            rhs = sts.r.copy()
+            Lo = ora.SpMatrix.synth(ora.GEN_LAPLACE2D, gs * gs, 5, 0, gs)
+            xo_ = ora.SpVector.synth(3, gs * gs)
+            bo_ = Lo.matVec(xo_)
+            x0o = ora.SpVector.mkSpVR(gs * gs, np.zeros(gs * gs))
+            sto = ora.bicgsInit(Lo, bo_, x0o)
+            rho_ = bo_ - Lo.matVec(x0o)
+            worst = 0.0
+            for _ in range(5):
+                sla.bicgstabStep(Ls, rhs, sts)
+                sto = ora.bicgstabStep(Lo, rho_, sto)
+                xr_ = np.asarray(sto.x.toDenseListSV())
+                worst = max(worst, float(np.abs(sts.x.toDenseListSV() - xr_[ss[rank]:ss[rank + 1]]).max() / max(np.abs(xr_).max(), 1e-300)))
+            extra["bicgstab_small_vs_oracle"] = {"grid": gs, "steps": 5, "max_rel_diff": max_over_ranks(worst), "ok": max_over_ranks(worst) <= 1e-10}
+            del Ls, sts
         if world == 1 and "sptrsv" in want:
             sptrsv_extra("cfg3", L3, b)
         del L3, st
@@ -354,7 +502,28 @@ def run_gpu(args):
         extra["arnoldi_cfg4_steps_per_s"] = 30 / s4
         extra["arnoldi_cfg4_ms_per_cycle"] = s4 * 1e3
         extra["arnoldi_cfg4_gbs"] = b4bytes / s4 / 1e9
-        del A4, Qd
+        extra["cfg4_x_exchange_mode"] = getattr(A4, "dist_p2p_mode", 0)
+        del Qd
+        # GMRES(30), 10 restarts (BASELINE.json config 4): fixed work, 300 Arnoldi steps with one re-orthogonalisation pass each,
+        # 10 restart residuals and 10 solution updates; the stopping test is off so that every cycle runs to its end.
+        x04 = sla.SpVector.zeroSV(A4.row_starts[rank + 1] - A4.row_starts[rank])
+        sla.gmres(A4, b4, x04, restart=30, nits=30, fixed_work=True)          # warm-up cycle
+        sg4, samples4 = float("inf"), []
+        for _ in range(2):                                  # best of two runs of 10 cycles (both reported)
+            barrier()
+            t0 = time.perf_counter()
+            xg4, itg4, resg4 = sla.gmres(A4, b4, x04, restart=30, nits=300, fixed_work=True, info=True)
+            barrier()
+            samples4.append(max_over_ranks(time.perf_counter() - t0))
+            sg4 = min(sg4, samples4[-1])
+        g4bytes = 10 * (31 * spmv_bytes(n4, n4 * k4) + 17096 * n4)      # per cycle: 31 (#>) + two projection passes per step
+        extra["gmres_cfg4_cycles_per_s"] = 10 / sg4
+        extra["gmres_cfg4_ms_per_cycle"] = sg4 * 1e2
+        extra["gmres_cfg4_gbs"] = g4bytes / sg4 / 1e9
+        extra["gmres_cfg4_seconds_per_10_cycles"] = samples4
+        extra["gmres_cfg4_iters"] = itg4
+        extra["gmres_cfg4_final_residual"] = resg4
+        del A4, xg4
     if "cfg5" in want:
         # ---- config 5: (##) CSR 10M x 10M x dense 10M x 128 bf16 (single GPU here; the row-partitioned (##) exists but has not
         # been run on hardware yet, so it stays out of the default multi-GPU line).
@@ -372,9 +541,12 @@ def run_gpu(args):
                 extra[f"spmm_cfg5_{tag}_gbs"] = b5 / (ms5 * 1e-3) / 1e9
                 extra[f"spmm_cfg5_{tag}_tflops"] = 2 * A5.nnz * k5 / (ms5 * 1e-3) / 1e12
                 del A5
+            extra["spmm_cfg5_uniform_note"] = ("uniform columns: adjacent rows share no B rows, so the kernel really moves ~82 GB of gathered B rows "
+                                               "(11.6x the 7.08 GB algorithmic count, at the L2 bandwidth) — the low fraction is traffic, not idleness")
             del B5, C5
-        elif os.environ.get("SLA_BENCH_DIST_SPMM") == "1":
-            # row-partitioned (##): written after the round-1 GPU budget was spent, so it is opt-in and can never cost the line
+        else:
+            # row-partitioned (##), K16 family: every rank holds its row slice of B; the rows of B the block references are
+            # gathered with the x-exchange plan applied to k-wide rows, then the tcgen05 tile path runs on the local block
             try:
                 k5 = 128
                 A5 = gen(sla.GEN_BLOCK16, n, 32, 0x5EED0005)
@@ -389,6 +561,19 @@ def run_gpu(args):
                 del A5, B5, C5
             except Exception as e:
                 extra["spmm_cfg5_dist_error"] = str(e)[:200]
+
+    if "cusparse" in want and world == 1:
+        # same-box context: cusparseSpMV (CSR, fp64) on the headline matrix; nothing of the product path uses it
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import cusparse_ref
+
+            cz = cusparse_ref.measure("uniform", reps=10)
+            extra["cusparse_spmv_cfg2"] = {kk: vv for kk, vv in cz.items() if kk.startswith("cusparse") or kk == "error"}
+        except Exception as e:
+            extra["cusparse_spmv_cfg2"] = {"error": str(e)[:200]}
+    if os.path.exists(os.path.join(ROOT, "profiles", "r02_gather_paths.jsonl")):
+        extra["gather_port_microbench"] = "profiles/r02_gather_paths.jsonl: 0.954 random 8-byte gathers per SM-cycle through LDG (= 277 G/s); cfg 2 needs 320 M per (#>)"
 
     if rank != 0:
         if dist is not None:
@@ -416,12 +601,16 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
                      "traffic": load_traffic()[0] if world == 1 else None,     # the ncu capture is of the single-GPU step
                      "traffic_per_launch": load_traffic()[1] if world == 1 else None, "launches_per_step": load_traffic()[2],
+                     "traffic_source": load_traffic()[3],
                      "traffic_note": "achieved and traffic are per STEP = one (#>) = launches_per_step launches of the kernel",
                      "peak_source": peak_src, "per_gpu": True,
                      "kernel": "spmv_tile_kernel<1024, EPI_NONE> (one launch per column panel, 2 panels at n = 10M)"},
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8 * nloc, "d2h_bytes_per_step": 8 * nloc,
                 "ms_per_step": e2e_s * 1e3, "api": "sla_spmv_host (pinned host buffers, per-rank slices)"},
         "gpu_launches": int(launches),
+        "parity_check": parity,
+        "step_ms": step_stats,
+        "x_exchange": xch,
         "clocks": clocks,
         "cpu_baseline": cpu,
         "extra": extra,
@@ -438,8 +627,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip the banded / BiCGSTAB context runs")
-    ap.add_argument("--extras", default="sptrsv,banded,cfg3,cfg4,cfg5",
-                    help="comma list of the context runs to include (sptrsv, banded, cfg3, cfg4, cfg5)")
+    ap.add_argument("--extras", default="sptrsv,banded,cfg3,cfg4,cfg5,cusparse",
+                    help="comma list of the context runs to include (sptrsv, banded, cfg3, cfg4, cfg5, cusparse)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sptrsv", action="store_true", help="skip the triangular-sweep context numbers")
     args = ap.parse_args()

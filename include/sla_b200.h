@@ -66,6 +66,8 @@ void*       sla_stream(sla_ctx*);                  /* the cudaStream_t every ker
 int         sla_rank(const sla_ctx*);
 int         sla_world(const sla_ctx*);
 int64_t     sla_launch_count(const sla_ctx*);      /* kernels launched by this ctx so far */
+/* named integer switches; "skip_exchange" = 1 is a DIAGNOSTIC for bench.py (row-partitioned (#>) without its x exchange) */
+sla_status  sla_set_option(sla_ctx*, const char* name, int64_t value);
 /* page-locked host buffers for the host-pointer entry points (Haskell: wrap in a ForeignPtr with sla_host_free) */
 sla_status  sla_host_alloc(sla_ctx*, int64_t bytes, void** out);
 void        sla_host_free(void*);
@@ -100,9 +102,12 @@ sla_status sla_p2p_export(sla_ctx*, void* handle64);
 sla_status sla_p2p_attach(sla_ctx*, const void* handles /* world x 64 bytes */);
 sla_status sla_p2p_enable(sla_ctx*, int on);
 int        sla_p2p_enabled(const sla_ctx*);
+/* LL halo exchange (mode 3): base[s] belongs to segment s of the plan given to sla_csr_set_dist — the compact offset of the
+ * segment in this rank's halo buffer (receive) or in the destination's (send).  Call before sla_csr_p2p_export. */
+sla_status sla_csr_set_halo(sla_ctx*, sla_csr*, int nseg, const int64_t* base);
 sla_status sla_csr_p2p_export(sla_ctx*, sla_csr*, void* handle64);
 sla_status sla_csr_p2p_attach(sla_ctx*, sla_csr*, const void* handles /* world x 64 bytes */);
-sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on /* 0 off, 1 push kernel, 2 copy engines + arrival-order panels */);
+sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on /* 0 off, 1 push kernel, 2 copy engines + arrival-order panels, 3 LL halo */);
 int        sla_csr_p2p_mode(const sla_csr*);      /* the mode in force (2 falls back to 1 when the plan is not dense / equal-block) */
 /* transposeSM of a row-partitioned square matrix (all-to-all of entries; starts = world + 1 global row offsets, the same on
  * every rank): *out is this rank's row block of the transpose; give it an exchange plan like any block, then hand it to A
@@ -192,6 +197,13 @@ sla_status sla_dense_from_host(sla_ctx*, int64_t rows, int64_t cols, const doubl
 sla_status sla_dense_generate(sla_ctx*, int64_t rows, int64_t cols, uint64_t seed, int dtype, sla_dense** out); /* synthetic, on-device */
 sla_status sla_dense_to_host_f64(sla_ctx*, const sla_dense*, double* rowmajor_out);
 sla_status sla_spmm_dense(sla_ctx*, const sla_csr* A, const sla_dense* B, sla_dense* C);
+/* the rest of MatrixRing (Class.hs:195-207; instance SpMatrix.hs:751-773) for a dense right operand, single GPU:
+ *   (##^)  a ## transpose b : Bt is the k x n row-major block whose TRANSPOSE is multiplied (matMat_ ABt, SpMatrix.hs:787-791)
+ *   (#^#)  transpose a ## b : B is m x k, C is n x k; A's transpose is built once and cached (as for (<#))
+ *   normFrobenius = sqrt (trace (m ##^ m)) : per row the left fold of a_ij * a_ij, then the sum over the rows (SpMatrix.hs:751-752) */
+sla_status sla_spmm_dense_abt(sla_ctx*, const sla_csr* A, const sla_dense* Bt, sla_dense* C);
+sla_status sla_spmm_dense_atb(sla_ctx*, const sla_csr* A, const sla_dense* B, sla_dense* C);
+sla_status sla_csr_norm_frobenius(sla_ctx*, const sla_csr* A, double* out);
 
 /* ---- preconditioners and triangular solves -------------------------------
  * Single GPU (a row-partitioned matrix returns SLA_ERR_INVALID).  New matrices are owned by the caller.
@@ -224,6 +236,7 @@ sla_status sla_tri_analysis(sla_ctx*, const sla_csr* A, int upper, int* nlevels,
 /* ---- dense blocks -------------------------------------------------------------------------- */
 sla_status sla_dense_dims(const sla_dense*, int64_t* rows, int64_t* cols);
 sla_status sla_dense_to_host(sla_ctx*, const sla_dense*, double* out_colmajor);
+sla_status sla_dense_column(sla_ctx*, const sla_dense* Q, int64_t j, sla_vec** out);   /* column j of the Arnoldi basis as a new vector (extractCol, SpMatrix.hs:329-337) */
 void       sla_dense_free(sla_dense*);
 
 #ifdef __cplusplus

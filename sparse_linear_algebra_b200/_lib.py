@@ -46,6 +46,7 @@ SIGNATURES = {
     "sla_rank": (C.c_int, [_p]),
     "sla_world": (C.c_int, [_p]),
     "sla_launch_count": (_i64, [_p]),
+    "sla_set_option": (C.c_int, [_p, C.c_char_p, _i64]),
     "sla_host_alloc": (C.c_int, [_p, _i64, _pp]),
     "sla_host_free": (None, [_p]),
     "sla_timer_start": (C.c_int, [_p]),
@@ -56,6 +57,7 @@ SIGNATURES = {
     "sla_csr_generate_rows": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_uint64, _i64, _i64, _i64, _pp]),
     "sla_csr_col_range": (C.c_int, [_p, _p, _pi64, _pi64]),
     "sla_csr_set_dist": (C.c_int, [_p, _p, _i64, C.c_int, _pint, _pint, _pi64, _pi64, C.c_int]),
+    "sla_csr_set_halo": (C.c_int, [_p, _p, C.c_int, _pi64]),
     "sla_csr_transpose_dist": (C.c_int, [_p, _p, _pi64, _pp]),
     "sla_csr_attach_transpose": (C.c_int, [_p, _p, _p]),
     "sla_p2p_export": (C.c_int, [_p, _p]),
@@ -113,6 +115,10 @@ SIGNATURES = {
     "sla_dense_generate": (C.c_int, [_p, _i64, _i64, C.c_uint64, C.c_int, _pp]),
     "sla_dense_to_host_f64": (C.c_int, [_p, _p, _pf64]),
     "sla_spmm_dense": (C.c_int, [_p, _p, _p, _p]),
+    "sla_spmm_dense_abt": (C.c_int, [_p, _p, _p, _p]),
+    "sla_spmm_dense_atb": (C.c_int, [_p, _p, _p, _p]),
+    "sla_csr_norm_frobenius": (C.c_int, [_p, _p, _pf64]),
+    "sla_dense_column": (C.c_int, [_p, _p, _i64, _pp]),
     "sla_csr_diag_partitions": (C.c_int, [_p, _p, _pp, _pp, _pp]),
     "sla_jacobi_pre": (C.c_int, [_p, _p, _pp]),
     "sla_mssor_pre": (C.c_int, [_p, _p, _f64, _pp, _pp]),

@@ -35,6 +35,7 @@ static sla_status ctx_create(int device, int rank, int world, sla_ctx** out) {
   c->spmv_hints = 3;
   if (const char* h = getenv("SLA_SPMV_HINTS")) c->spmv_hints = atoi(h);
   if (const char* h = getenv("SLA_SPMV_TMA")) c->spmv_tma = atoi(h);
+  if (const char* h = getenv("SLA_SPMV_BULK")) c->spmv_bulk = atoi(h);
   SLA_CUDA(c, cudaSetDevice(device));
   SLA_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   SLA_CUDA(c, cudaEventCreate(&c->ev0));
@@ -71,6 +72,7 @@ extern "C" void sla_finalize(sla_ctx* c) {
   cudaStreamSynchronize(c->stream);
   sla_p2p_free(c);
   cudaFree(c->bfull); c->bfull = nullptr; c->bfull_bytes = 0;
+  cudaFree(c->dense_cache); c->dense_cache = nullptr; c->dense_cache_bytes = 0;
   for (int k = 0; k < c->n_parked; ++k) cudaFree(c->parked[k]);
   c->n_parked = 0;
   if (c->nccl) sla_dist_detach(c);
@@ -94,6 +96,16 @@ extern "C" void* sla_stream(sla_ctx* c) { return c ? (void*)c->stream : nullptr;
 extern "C" int sla_rank(const sla_ctx* c) { return c ? c->rank : 0; }
 extern "C" int sla_world(const sla_ctx* c) { return c ? c->world : 1; }
 extern "C" int64_t sla_launch_count(const sla_ctx* c) { return c ? c->launches : 0; }
+
+// Named integer switches of a context.  "skip_exchange" = 1: the row-partitioned (#>) launches its kernels without exchanging x
+// first — a DIAGNOSTIC that lets bench.py time the kernels alone (exposed exchange time = step time - this); results are invalid.
+extern "C" sla_status sla_set_option(sla_ctx* c, const char* name, int64_t value) {
+  if (!c || !name) return SLA_ERR_INVALID;
+  if (strcmp(name, "skip_exchange") == 0) { c->skip_exchange = value != 0; return SLA_OK; }
+  if (strcmp(name, "spmv_hints") == 0) { c->spmv_hints = (int)value; return SLA_OK; }
+  if (strcmp(name, "spmv_bulk") == 0) { c->spmv_bulk = value != 0; return SLA_OK; }
+  return sla_fail(c, SLA_ERR_INVALID, "sla_set_option: unknown option");
+}
 
 extern "C" sla_status sla_host_alloc(sla_ctx* c, int64_t bytes, void** out) {
   if (!c || !out || bytes < 0) return SLA_ERR_INVALID;
@@ -344,6 +356,6 @@ extern "C" sla_status sla_dense_to_host(sla_ctx* c, const sla_dense* d, double* 
 
 extern "C" void sla_dense_free(sla_dense* d) {
   if (!d) return;
-  if (d->d) { cudaStreamSynchronize(d->ctx->stream); cudaFree(d->d); }
+  sla_pool_free(d->ctx, d->d, d->bytes);
   delete d;
 }

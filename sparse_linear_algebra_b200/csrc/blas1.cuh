@@ -18,7 +18,7 @@ template <int N> struct Ptrs { double* p[N > 0 ? N : 1]; };
 template <class OP>
 __global__ void __launch_bounds__(EW_THREADS)
 ew_kernel(OP op, int64_t n, Ptrs<OP::NIN> in, Ptrs<OP::NOUT> out, double* scal, double* partials,
-          unsigned int* counter, int fin, int dst) {
+          unsigned int* counter, int fin, int dst, sla_p2p_args pa) {
   constexpr int NIN = OP::NIN, NOUT = OP::NOUT, NRED = OP::NRED;
   __shared__ double red[(NRED > 0 ? NRED : 1) * 32];
   op.prep(scal);
@@ -52,7 +52,7 @@ ew_kernel(OP op, int64_t n, Ptrs<OP::NIN> in, Ptrs<OP::NOUT> out, double* scal, 
   }
   if (NRED > 0) {
     block_sum<(NRED > 0 ? NRED : 1)>(acc, red);
-    grid_reduce_finish<(NRED > 0 ? NRED : 1)>(acc, partials, counter, scal, fin, dst, red);
+    grid_reduce_finish<(NRED > 0 ? NRED : 1)>(acc, partials, counter, scal, fin, dst, red, pa);
   }
 }
 
@@ -62,10 +62,11 @@ static inline sla_status ew_launch(sla_ctx* c, OP op, int64_t n, Ptrs<OP::NIN> i
   int64_t blocks = ((n >> 1) + EW_THREADS - 1) / EW_THREADS;
   if (blocks < 1) blocks = 1;
   if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;
-  ew_kernel<OP><<<(unsigned)blocks, EW_THREADS, 0, c->stream>>>(op, n, in, out, c->scal, c->partials, c->counter,
-                                                                OP::NRED > 0 ? fin_for(c, fin) : fin, dst);
+  sla_red_plan rp = sla_red_begin(c, fin, OP::NRED > 0 ? OP::NRED : P2P_MAX_NV + 1);   // kernels without a reduction never take a sequence number
+  if (OP::NRED == 0) { rp.fin = fin; rp.host = false; }
+  ew_kernel<OP><<<(unsigned)blocks, EW_THREADS, 0, c->stream>>>(op, n, in, out, c->scal, c->partials, c->counter, rp.fin, dst, rp.pa);
   SLA_LAUNCH_CHECK(c);
-  if (OP::NRED > 0) SLA_TRY(sla_dist_finish_reduction(c, OP::NRED, fin, dst));
+  if (OP::NRED > 0) SLA_TRY(sla_red_end(c, rp, OP::NRED, fin, dst));
   return SLA_OK;
 }
 

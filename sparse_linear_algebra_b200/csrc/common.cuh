@@ -14,6 +14,7 @@
 #define SLA_MAX_PARTIALS (1 << 20)
 #define SLA_MAX_PANELS 64        // column panels per matrix (spmv.cu)
 #define SLA_MAX_WORLD 16         // ranks of one NVSwitch domain the peer-memory collectives address (p2p.cu)
+#define SLA_HALO_MAX_SEGS 8      // receive segments of an LL halo plan (p2p.cu mode 3)
 #define SLA_MAX_PARKED 256       // retired peer-memory windows kept until sla_finalize (p2p.cu)
 
 // device scalar slots (doubles living in ctx->scal)
@@ -44,11 +45,14 @@ struct sla_ctx {
   int spmv_hints;            // bit0: matrix stream L2 evict_first, bit1: x gathers L2 evict_last (env SLA_SPMV_HINTS)
   cudaStream_t copy_stream;  // PCIe copies of the pipelined host-buffer (#>) (spmv.cu)
   cudaEvent_t ev_copy[SLA_MAX_PANELS + 16];
+  int spmv_bulk;             // 1: the tile kernel stages its (col, val) tile with bulk copies instead of LDG (env SLA_SPMV_BULK / option "spmv_bulk")
   int spmv_tma;              // 0: LDG tile kernel; k > 0: TMA-staged persistent kernel with k CTAs per SM (env SLA_SPMV_TMA)
   const void* scal_owner;    // Krylov state whose recurrence scalars currently live in scal[]
   void* bfull; size_t bfull_bytes;   // gathered dense right operand of a row-partitioned (##) (spmm.cu / dist.cu)
   struct sla_p2p* p2p;       // peer-memory all-reduce window (p2p.cu); null / disabled: NCCL
   void* parked[SLA_MAX_PARKED]; int n_parked;   // exchange windows of freed matrices (peers may still map them)
+  void* dense_cache; size_t dense_cache_bytes;   // the last freed dense block (sla_pool_alloc / sla_pool_free)
+  int skip_exchange;         // diagnostic (sla_set_option "skip_exchange"): row-partitioned (#>) runs its kernels WITHOUT the x exchange (results invalid)
   char err[512];
 };
 
@@ -80,6 +84,10 @@ struct sla_dist_info {
   int pan_first[SLA_MAX_PANELS + 1];   // pseg[pan_first[p] .. pan_first[p+1]) belong to panel p
   sla_xseg* pseg;
   struct sla_xwin* xwin;     // peer-memory exchange window (p2p.cu); when enabled xfull points into it
+  // LL halo plan (p2p.cu mode 3), installed by sla_csr_set_halo: compact index of every segment — for a receive segment the
+  // offset of its first entry in THIS rank's halo buffer, for a send segment its offset in the DESTINATION's
+  int64_t* seg_base;         // nseg entries, null: no halo plan
+  int64_t halo_total;        // entries this rank receives per exchange
 };
 
 struct sla_csr {
@@ -111,6 +119,7 @@ static inline int64_t csr_xdim(const sla_csr* A) { return A->dist ? A->m : A->n;
 
 struct sla_dense {
   sla_ctx* ctx;
+  size_t bytes;              // size of the allocation behind d
   int64_t rows, cols, ld;    // column-major (Krylov basis): ld = rows rounded up to 16 doubles; row-major (## operands): ld = cols
   int dtype, rowmajor;       // SLA_F64 / SLA_BF16 ; 1 = row-major block created by sla_dense_create
   double* d;
@@ -236,12 +245,80 @@ __device__ __forceinline__ void finalize_scalars(int fin, int dst, double* scal,
   }
 }
 
+// ---- peer-memory all-reduce, inlined into the kernel that ends a grid reduction (p2p.cu owns the windows) -------------
+// Window of a context: flags[b][r] (u64) at byte 8 * (b * SLA_MAX_WORLD + r), values[b][r][k] at byte
+// P2P_FLAG_BYTES + 8 * ((b * SLA_MAX_WORLD + r) * P2P_MAX_NV + k); b = sequence parity (double buffer).
+#define P2P_FLAG_BYTES 256
+#define P2P_MAX_NV 32                            // doubles per all-reduce (one chunk of Arnoldi dots)
+#define P2P_TIMEOUT_CYCLES 60000000000LL         // ~30 s at 1.9 GHz
+
+struct sla_p2p_args {          // world <= 1: the reduction is local (or completed by the host through NCCL)
+  char* const* peer;           // device array: every rank's window as mapped here
+  int* err;                    // device flag: a wait timed out
+  unsigned long long seq;
+  int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// spins until *p >= seq; false (and *err = 1) when the peer never shows up
+__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long seq, int* err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys_u64(p) < seq) {
+    if (clock64() - t0 > P2P_TIMEOUT_CYCLES) { atomicExch(err, 1); return false; }
+  }
+  return true;
+}
+
+// All threads of ONE CTA (>= world threads): vals[0..nv) (shared memory) holds this rank's sums on entry and the sums over
+// all ranks — added in RANK ORDER, hence bit-identical on every rank — on exit.
+__device__ __forceinline__ void p2p_allreduce_block(const sla_p2p_args& a, double* vals, int nv) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int b = (int)(a.seq & 1ull);
+  const int slot = b * SLA_MAX_WORLD + a.rank;
+  for (int q = t; q < a.world * nv; q += nt) {                      // (peer, value) pairs
+    const int p = q / nv, k = q - p * nv;
+    st_relaxed_sys_f64(reinterpret_cast<double*>(a.peer[p] + P2P_FLAG_BYTES) + (size_t)slot * P2P_MAX_NV + k, vals[k]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  char* mine = a.peer[a.rank];
+  if (t < a.world) {
+    __threadfence_system();                                         // cumulative over the CTA's stores observed through the barrier
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(a.peer[t]) + slot, a.seq);
+    wait_flag(reinterpret_cast<const unsigned long long*>(mine) + b * SLA_MAX_WORLD + t, a.seq, a.err);
+  }
+  __syncthreads();
+  double s = 0.0;
+  if (t < nv) {
+    const double* in = reinterpret_cast<const double*>(mine + P2P_FLAG_BYTES) + (size_t)b * SLA_MAX_WORLD * P2P_MAX_NV;
+    for (int r = 0; r < a.world; ++r) s += ld_relaxed_sys_f64(in + (size_t)r * P2P_MAX_NV + t);
+  }
+  __syncthreads();
+  if (t < nv) vals[t] = s;
+  __syncthreads();
+}
+
 // Deterministic grid reduction: every CTA writes its NV partials, takes a ticket; the last CTA sums all
 // partials in a fixed order (thread-strided sequential, then the block tree) and post-processes scalars.
 // Must be called by all threads of every CTA.  `mine` holds this CTA's sums in thread 0.
 template <int NV>
 __device__ __forceinline__ void grid_reduce_finish(double (&mine)[NV], double* partials, unsigned int* counter,
-                                                   double* scal, int fin, int dst, double* smem) {
+                                                   double* scal, int fin, int dst, double* smem, const sla_p2p_args& pa) {
   __shared__ bool is_last;
   const unsigned int nblk = gridDim.x;
   if (threadIdx.x == 0) {
@@ -263,6 +340,21 @@ __device__ __forceinline__ void grid_reduce_finish(double (&mine)[NV], double* p
   }
   __syncthreads();
   block_sum<NV>(acc, smem);
+  if (pa.world > 1) {
+    // multi-GPU: the last CTA completes the reduction itself over NVLink peer memory — no separate all-reduce launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) smem[k] = acc[k];
+    }
+    __syncthreads();
+    p2p_allreduce_block(pa, smem, NV);
+    if (threadIdx.x == 0) {
+      finalize_scalars(fin & 0xff, dst, scal, smem, NV);
+      *counter = 0u;
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     if (fin & FIN_DEFER) {
       const int base = (fin & 0xff) == FIN_STORE ? dst : S_RAW;
@@ -273,6 +365,40 @@ __device__ __forceinline__ void grid_reduce_finish(double (&mine)[NV], double* p
     }
     *counter = 0u;
   }
+}
+
+// where the (#>) kernel of a row block finds the x entries of remote columns (spmv.cu)
+struct SpmvDist {
+  const double* xr;          // gathered-x buffer, indexed by GLOBAL column
+  int col0, ncl;             // local column range [col0, col0 + ncl): read from the local slice instead
+};
+
+// Dense blocks (the Arnoldi basis is ~1 GB at cfg 4): the context keeps the last freed block and hands it to the next
+// request it fits, so that back-to-back arnoldi / gmres calls do not make the driver unmap and re-map a gigabyte each time
+// (measured: 3-5 ms of a 41 ms arnoldi(A, b, 30) went there).  All users are ordered on the context stream, so no
+// synchronisation is needed for the hand-over.  (cudaMallocAsync was tried first: 38-372 ms per call, erratic.)
+static inline cudaError_t sla_pool_alloc(sla_ctx* c, void** p, size_t bytes) {
+  if (bytes < 16) bytes = 16;
+  if (c->dense_cache && c->dense_cache_bytes >= bytes && c->dense_cache_bytes <= 2 * bytes + (1u << 20)) {
+    *p = c->dense_cache; c->dense_cache = nullptr; c->dense_cache_bytes = 0;
+    return cudaSuccess;
+  }
+  const cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaSuccess) return e;
+  cudaGetLastError();
+  if (c->dense_cache) { cudaStreamSynchronize(c->stream); cudaFree(c->dense_cache); c->dense_cache = nullptr; c->dense_cache_bytes = 0; }
+  return cudaMalloc(p, bytes);
+}
+static inline void sla_pool_free(sla_ctx* c, void* p, size_t bytes) {
+  if (!p) return;
+  if (bytes >= (8u << 20) && bytes > c->dense_cache_bytes) {        // keep the larger block
+    void* old = c->dense_cache;
+    c->dense_cache = p; c->dense_cache_bytes = bytes;
+    p = old;
+    if (!p) return;
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaFree(p);
 }
 
 // internal entry points shared between translation units
@@ -303,7 +429,7 @@ sla_status sla_p2p_allreduce(sla_ctx* c, int nv, int src, int fin, int dst);
 sla_status sla_p2p_check(sla_ctx* c);
 void sla_p2p_free(sla_ctx* c);
 bool sla_xwin_active(const sla_csr* A);
-int sla_xwin_mode(const sla_csr* A);                                                             // 0 off, 1 push kernel, 2 arrival order
+int sla_xwin_mode(const sla_csr* A);                                                             // 0 off, 1 push kernel, 2 arrival order, 3 LL halo, 4 copy-engine all-gather
 sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_local);
 sla_status sla_p2p_arrival_wait(sla_ctx* c, const sla_csr* A, int src);
 sla_status sla_p2p_arrival_end(sla_ctx* c);
@@ -311,7 +437,24 @@ sla_status sla_p2p_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_loca
 void sla_xwin_free(sla_csr* A);
 void sla_csr_free_bsr(sla_csr* A);
 void sla_csr_free_tri(sla_csr* A);                                                                // trisolve.cu
-static inline int fin_for(const sla_ctx* c, int fin) { return c->world > 1 ? (fin | FIN_DEFER) : fin; }
+// How the kernel that ends a grid reduction completes it across ranks: inline over peer memory (pa.world > 1), or raw sums
+// + an all-reduce issued by the host (NCCL, or the stand-alone peer kernel) when `host` is set; single GPU: neither.
+struct sla_red_plan { int fin; sla_p2p_args pa; bool host; };
+sla_p2p_args sla_p2p_next(sla_ctx* c);                                                           // p2p.cu: args of the next inline all-reduce (bumps the sequence)
+bool sla_p2p_inline(const sla_ctx* c);
+static inline sla_red_plan sla_red_begin(sla_ctx* c, int fin, int nv) {
+  sla_red_plan r;
+  r.fin = fin; r.host = false;
+  r.pa.peer = nullptr; r.pa.err = nullptr; r.pa.seq = 0; r.pa.rank = 0; r.pa.world = 1;
+  if (c->world > 1) {
+    if (nv <= P2P_MAX_NV && sla_p2p_inline(c)) r.pa = sla_p2p_next(c);
+    else { r.fin = fin | FIN_DEFER; r.host = true; }
+  }
+  return r;
+}
+static inline sla_status sla_red_end(sla_ctx* c, const sla_red_plan& r, int nv, int fin, int dst) {
+  return r.host ? sla_dist_finish_reduction(c, nv, fin, dst) : SLA_OK;
+}
 
 // SpMV epilogues
 enum {

@@ -168,6 +168,7 @@ void sla_csr_free_dist(sla_csr* A) {
   cudaFree(A->dist->xfull);
   delete[] A->dist->seg;
   delete[] A->dist->pseg;
+  delete[] A->dist->seg_base;
   delete A->dist;
   A->dist = nullptr;
 }
@@ -182,7 +183,7 @@ extern "C" sla_status sla_csr_set_dist(sla_ctx* c, sla_csr* A, int64_t row0, int
   sla_csr_free_dist(A);
   sla_dist_info* d = new (std::nothrow) sla_dist_info();
   if (!d) return sla_fail(c, SLA_ERR_ALLOC, "set_dist alloc");
-  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0; d->dense_equal = 0; d->pipelined = 0; d->pseg = nullptr; d->xwin = nullptr;
+  d->row0 = row0; d->nseg = nseg; d->xfull = nullptr; d->allgather = 0; d->dense_equal = 0; d->pipelined = 0; d->pseg = nullptr; d->xwin = nullptr; d->seg_base = nullptr; d->halo_total = 0;
   d->seg = new sla_xseg[nseg > 0 ? nseg : 1];
   for (int s = 0; s < nseg; ++s) {
     if (peer[s] < 0 || peer[s] >= c->world || peer[s] == c->rank || goff[s] < 0 || count[s] < 0 || goff[s] + count[s] > A->n ||

@@ -341,39 +341,92 @@ extern "C" sla_status sla_linsolve0_host(sla_ctx* c, int method, const sla_csr* 
 // read and written by the projection, read again by the scaling that writes q_{j+1}.
 
 #define TS_NC 32   // basis columns per launch of the tall-skinny dot kernel
+#define TS_WARPS (EW_THREADS / 32)
+#define TS_CPW (TS_NC / TS_WARPS)   // columns per warp
+#define TS_UNROLL 2
 
-// h[k0 + k] = q_{k0+k} <.> w   for k < nc <= NC        (hhcoli = fmap (`dot` aqi) qv, Sparse.hs:655)
-template <int NC>
-__global__ void __launch_bounds__(EW_THREADS)
+// h[k0 + k] = q_{k0+k} <.> w   for k < nc <= TS_NC        (hhcoli = fmap (`dot` aqi) qv, Sparse.hs:655)
+// A CTA walks 512-byte pieces of the vectors; its 8 warps split the COLUMNS (warp v owns columns v, v + 8, v + 16, v + 24), so a
+// thread carries 4 accumulators instead of 32 — the first version (every thread, every column) needed 128 registers, ran at
+// 25 % occupancy with 64 KB of loads in flight per SM and reached 4.6 TB/s (profiles/r02_arnoldi_kernels.txt); w is read by
+// all 8 warps but only the first read of a piece leaves the SM.  No cross-warp reduction is needed: a column belongs to one warp.
+__global__ void __launch_bounds__(EW_THREADS, 4)
 tsmv_t_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int k0, int nc, const double* __restrict__ w,
-              double* scal, double* partials, unsigned int* counter, int fin, int slot0) {
-  __shared__ double red[NC * 32];
-  double acc[NC];
+              double* scal, double* partials, unsigned int* counter, int fin, int slot0, sla_p2p_args pa) {
+  __shared__ double colsum[TS_NC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[TS_CPW];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) acc[k] = 0.0;
-  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int q = 0; q < TS_CPW; ++q) acc[q] = 0.0;
+  const int64_t n2 = n >> 1, ld2 = ld >> 1;                         // ld is a multiple of 16 doubles
   const double2* Q2 = reinterpret_cast<const double2*>(Q + (int64_t)k0 * ld);
-  const int64_t ld2 = ld >> 1;                        // ld is a multiple of 16 doubles
-  for (int64_t i = gtid; i < n2; i += stride) {
-    const double2 wv = reinterpret_cast<const double2*>(w)[i];
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  const int64_t step = (int64_t)gridDim.x * 32;
+  int64_t i = (int64_t)blockIdx.x * 32 + lane;
+#pragma unroll 1
+  for (; i + (TS_UNROLL - 1) * step < n2; i += TS_UNROLL * step) {     // TS_UNROLL pieces per trip: 8 + 2 loads in flight per thread
+    double2 wv[TS_UNROLL], qv[TS_UNROLL][TS_CPW];
 #pragma unroll
-    for (int kb = 0; kb < NC; kb += 8) {
-      if (kb < nc) {                                  // warp-uniform
-        double2 q[8];
+    for (int u = 0; u < TS_UNROLL; ++u) {
+      wv[u] = w2[i + u * step];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (kb + k < nc) q[k] = Q2[(int64_t)(kb + k) * ld2 + i];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (kb + k < nc) { acc[kb + k] += q[k].x * wv.x; acc[kb + k] += q[k].y * wv.y; }
-      }
+      for (int q = 0; q < TS_CPW; ++q)
+        if (warp + q * TS_WARPS < nc) qv[u][q] = Q2[(int64_t)(warp + q * TS_WARPS) * ld2 + i + u * step];
     }
+#pragma unroll
+    for (int u = 0; u < TS_UNROLL; ++u)
+#pragma unroll
+      for (int q = 0; q < TS_CPW; ++q)
+        if (warp + q * TS_WARPS < nc) { acc[q] += qv[u][q].x * wv[u].x; acc[q] += qv[u][q].y * wv[u].y; }
   }
-  if ((n & 1) && gtid == 0) {
-    for (int k = 0; k < nc; ++k) acc[k] += Q[(int64_t)(k0 + k) * ld + n - 1] * w[n - 1];
+#pragma unroll 1
+  for (; i < n2; i += step) {
+    const double2 wv = w2[i];
+#pragma unroll
+    for (int q = 0; q < TS_CPW; ++q)
+      if (warp + q * TS_WARPS < nc) {
+        const double2 qv = Q2[(int64_t)(warp + q * TS_WARPS) * ld2 + i];
+        acc[q] += qv.x * wv.x; acc[q] += qv.y * wv.y;
+      }
   }
-  block_sum<NC>(acc, red);
-  grid_reduce_finish<NC>(acc, partials, counter, scal, fin, slot0 + k0, red);
+  if ((n & 1) && blockIdx.x == 0 && lane == 0) {
+#pragma unroll
+    for (int q = 0; q < TS_CPW; ++q)
+      if (warp + q * TS_WARPS < nc) acc[q] += Q[(int64_t)(k0 + warp + q * TS_WARPS) * ld + n - 1] * w[n - 1];
+  }
+#pragma unroll
+  for (int q = 0; q < TS_CPW; ++q) {
+    acc[q] = warp_sum(acc[q]);
+    if (lane == 0) colsum[warp + q * TS_WARPS] = acc[q];
+  }
+  __syncthreads();
+  // grid reduction, one column per warp again: per-CTA sums -> ticket -> the last CTA adds them in a fixed order
+  // (lane-strided partial sums + shuffle tree), completes the all-reduce over peer memory when there are ranks, and stores
+  __shared__ bool is_last;
+  const unsigned int nblk = gridDim.x;
+  if (threadIdx.x < TS_NC) partials[(size_t)threadIdx.x * nblk + blockIdx.x] = colsum[threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == nblk - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < TS_CPW; ++q) {
+    const int k = warp + q * TS_WARPS;
+    const volatile double* p = partials + (size_t)k * nblk;
+    double s = 0.0;
+    for (unsigned int b = lane; b < nblk; b += 32) s += p[b];
+    s = warp_sum(s);
+    if (lane == 0) colsum[k] = s;
+  }
+  __syncthreads();
+  if (pa.world > 1) p2p_allreduce_block(pa, colsum, TS_NC);
+  if (threadIdx.x == 0) {
+    finalize_scalars(FIN_STORE, slot0 + k0, scal, colsum, TS_NC);    // with or without FIN_DEFER: the sums go to their slots
+    *counter = 0u;
+  }
+  (void)fin;
 }
 
 // out_i = base_i -/+ (((c_0 q_0i) + c_1 q_1i) + ... + c_{nc-1} q_{nc-1,i}), coefficients in scal[slot0..];
@@ -382,7 +435,7 @@ tsmv_t_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int k0, int n
 template <int SIGN>
 __global__ void __launch_bounds__(EW_THREADS)
 lincomb_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int nc, const double* base, double* out,
-               double* scal, double* partials, unsigned int* counter, int fin, int slot0, const int* nc_dev) {
+               double* scal, double* partials, unsigned int* counter, int fin, int slot0, const int* nc_dev, sla_p2p_args pa) {
   __shared__ double coef[SLA_MAX_KRYLOV + 2];
   __shared__ double red[32];
   if (nc_dev) { const int cap = *nc_dev; if (cap < nc) nc = cap; }
@@ -427,7 +480,7 @@ lincomb_kernel(const double* __restrict__ Q, int64_t ld, int64_t n, int nc, cons
   }
   if (SIGN < 0) {
     block_sum<1>(acc, red);
-    grid_reduce_finish<1>(acc, partials, counter, scal, fin, 0, red);
+    grid_reduce_finish<1>(acc, partials, counter, scal, fin, 0, red, pa);
   }
 }
 
@@ -527,27 +580,26 @@ static unsigned ts_blocks(int64_t n) {
   return (unsigned)b;
 }
 
-// grid of the tall-skinny dot kernel: whole waves of resident CTAs (its 2 NC accumulator registers limit the occupancy)
-template <int NC>
+// grid of the tall-skinny dot kernel: whole waves of resident CTAs
 static unsigned tsmv_grid(int64_t n) {
   static int per_sm = 0;
   if (!per_sm) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsmv_t_kernel<NC>, EW_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsmv_t_kernel, EW_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
   }
-  const unsigned cap = (unsigned)(SLA_NUM_SMS * per_sm), want = ts_blocks(n);
-  return want < cap ? want : cap;
+  int64_t want = ((n >> 1) + 32 * TS_UNROLL - 1) / (32 * TS_UNROLL);
+  if (want < 1) want = 1;
+  const int64_t cap = (int64_t)SLA_NUM_SMS * per_sm;
+  return (unsigned)(want < cap ? want : cap);
 }
 
 static sla_status tsmv_launch(sla_ctx* c, const sla_dense* Q, int nq, const double* w, int slot0) {
   const int64_t n = Q->rows, ld = Q->ld;
   for (int k0 = 0; k0 < nq; k0 += TS_NC) {
     const int nc = nq - k0 < TS_NC ? nq - k0 : TS_NC;
-    const int fin = fin_for(c, FIN_STORE);
-    if (nc <= 8) tsmv_t_kernel<8><<<tsmv_grid<8>(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, fin, slot0);
-    else if (nc <= 16) tsmv_t_kernel<16><<<tsmv_grid<16>(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, fin, slot0);
-    else tsmv_t_kernel<32><<<tsmv_grid<32>(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, fin, slot0);
+    const sla_red_plan rp = sla_red_begin(c, FIN_STORE, TS_NC);      // the kernel reduces all TS_NC slots (the unused ones are 0)
+    tsmv_t_kernel<<<tsmv_grid(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, k0, nc, w, c->scal, c->partials, c->counter, rp.fin, slot0, rp.pa);
     SLA_LAUNCH_CHECK(c);
-    SLA_TRY(sla_dist_finish_reduction(c, nc, FIN_STORE, slot0 + k0));
+    SLA_TRY(sla_red_end(c, rp, TS_NC, FIN_STORE, slot0 + k0));
   }
   return SLA_OK;
 }
@@ -558,7 +610,8 @@ static sla_status dense_alloc(sla_ctx* c, int64_t rows, int64_t cols, sla_dense*
   d->ctx = c; d->rows = rows; d->cols = cols; d->ld = (rows + 15) & ~(int64_t)15; d->d = nullptr;
   d->dtype = SLA_F64; d->rowmajor = 0;
   if (d->ld == 0) d->ld = 16;
-  if (cudaMalloc(&d->d, sizeof(double) * (size_t)d->ld * (size_t)(cols > 0 ? cols : 1)) != cudaSuccess) {
+  d->bytes = sizeof(double) * (size_t)d->ld * (size_t)(cols > 0 ? cols : 1);
+  if (sla_pool_alloc(c, (void**)&d->d, d->bytes) != cudaSuccess) {
     cudaGetLastError(); delete d;
     return sla_fail(c, SLA_ERR_ALLOC, "cudaMalloc failed for a dense block");
   }
@@ -578,9 +631,10 @@ static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j
   for (int pass = 0; pass < (reorth ? 2 : 1); ++pass) {
     const int slot0 = pass == 0 ? S_HCOL : S_HCOL2;
     SLA_TRY(tsmv_launch(c, Q, nq, w, slot0));
-    lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, fin_for(c, FIN_NORM_INV), slot0, nullptr);
+    const sla_red_plan rp = sla_red_begin(c, FIN_NORM_INV, 1);
+    lincomb_kernel<-1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, ld, n, nq, w, w, c->scal, c->partials, c->counter, rp.fin, slot0, nullptr, rp.pa);
     SLA_LAUNCH_CHECK(c);
-    SLA_TRY(sla_dist_finish_reduction(c, 1, FIN_NORM_INV, 0));
+    SLA_TRY(sla_red_end(c, rp, 1, FIN_NORM_INV, 0));
   }
   arn_finish_kernel<GM><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(w, Q->d + (int64_t)(j + 1) * ld, n, c->scal, j, reorth ? 1 : 0, d, tol, g0);
   SLA_LAUNCH_CHECK(c);
@@ -692,7 +746,7 @@ extern "C" sla_status sla_gmres(sla_ctx* c, const sla_csr* A, const sla_vec* b, 
     if (s != SLA_OK) break;
     // R y = g on the device, then x = x + Q[:, 0..jn-1] y
     gmres_solve_kernel<<<1, 32, 0, c->stream>>>(d, jmax, c->scal);
-    lincomb_kernel<1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, Q->ld, n, jmax, x->d, x->d, c->scal, c->partials, c->counter, FIN_STORE, S_HCOL, d.meta + 1);
+    lincomb_kernel<1><<<ts_blocks(n), EW_THREADS, 0, c->stream>>>(Q->d, Q->ld, n, jmax, x->d, x->d, c->scal, c->partials, c->counter, FIN_STORE, S_HCOL, d.meta + 1, sla_red_begin(c, FIN_STORE, P2P_MAX_NV + 1).pa);
     c->launches += 2;
     int meta[2] = {-1, 0};
     double rest = 0;

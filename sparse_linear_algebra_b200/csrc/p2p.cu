@@ -29,14 +29,12 @@
 #include "common.cuh"
 
 #include <new>
+#include <stdlib.h>
 
-#define P2P_FLAG_BYTES 256                       // flags live in the first 256 bytes of a window
-#define P2P_MAX_NV 32                            // doubles per all-reduce (one Hessenberg column chunk of the Arnoldi dots)
 #define P2P_AR_THREADS 128
 #define P2P_AR_WINDOW_BYTES (P2P_FLAG_BYTES + 2 * SLA_MAX_WORLD * P2P_MAX_NV * 8)   // [2][W] u64 flags | [2][W][P2P_MAX_NV] doubles
 #define P2P_ITEM_LEN 4096                        // doubles per push work item (one CTA)
 #define P2P_PUSH_THREADS 256
-#define P2P_TIMEOUT_CYCLES 60000000000LL         // ~30 s at 1.9 GHz
 
 struct p2p_item { int peer; int len; int64_t goff; int64_t src; };
 
@@ -52,75 +50,30 @@ struct sla_p2p {                                 // per context: the all-reduce 
 
 struct sla_xwin {                                // per distributed matrix: [256 B flags][x buffer 0][x buffer 1]
   int enabled;
-  int mode;                                      // 1: push kernel + wait for every peer; 2: copy engines, arrival-order panels
+  int mode;                                      // 1: push kernel + wait for every peer; 2: copy engines, arrival-order panels; 3: LL halo
+  int ll;                                        // the window holds LL halo buffers (16-byte tagged entries) instead of gathered-x buffers
   char* win;
   size_t buf_bytes;
   char* peer[SLA_MAX_WORLD];
   char** d_peer;
   p2p_item* d_items;
-  int nitems;
+  int nitems;                                    // send items; LL windows: followed by nrecv unpack items
+  int nrecv;
   unsigned int* d_ticket;
   unsigned long long seq;
 };
 
 namespace {
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
-  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// spins until *p >= seq; false (and *err = 1) when the peer never shows up
-__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long seq, int* err) {
-  const long long t0 = clock64();
-  while (ld_acquire_sys_u64(p) < seq) {
-    if (clock64() - t0 > P2P_TIMEOUT_CYCLES) { atomicExch(err, 1); return false; }
-  }
-  return true;
-}
-
 // ---- all-reduce + scalar post-processing -------------------------------------------------------------------
-// window: flags[b][r] at byte 8 * (b * SLA_MAX_WORLD + r), values[b][r][k] at byte 256 + 8 * ((b * SLA_MAX_WORLD + r) * P2P_MAX_NV + k)
+// stand-alone form (NCCL-free fallback when the inline path is switched off, SLA_P2P_INLINE=0): the raw sums sit in scal[src ..]
 __global__ void __launch_bounds__(P2P_AR_THREADS)
-p2p_allreduce_kernel(char* const* __restrict__ peer, int rank, int world, unsigned long long seq, int nv, int src,
-                     int fin, int dst, double* scal, int* err) {
+p2p_allreduce_kernel(sla_p2p_args a, int nv, int src, int fin, int dst, double* scal) {
   __shared__ double sum[P2P_MAX_NV];
-  const int t = threadIdx.x;
-  const int b = (int)(seq & 1ull);
-  const int slot = b * SLA_MAX_WORLD + rank;
-  for (int q = t; q < world * nv; q += P2P_AR_THREADS) {          // (peer, value) pairs
-    const int p = q / nv, k = q - p * nv;
-    st_relaxed_sys_f64(reinterpret_cast<double*>(peer[p] + P2P_FLAG_BYTES) + (size_t)slot * P2P_MAX_NV + k, scal[src + k]);
-  }
-  __threadfence_system();
+  if (threadIdx.x < nv) sum[threadIdx.x] = scal[src + threadIdx.x];
   __syncthreads();
-  char* mine = peer[rank];
-  if (t < world) {
-    __threadfence_system();                                       // cumulative over the CTA's stores observed through the barrier
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(peer[t]) + slot, seq);
-    wait_flag(reinterpret_cast<const unsigned long long*>(mine) + b * SLA_MAX_WORLD + t, seq, err);
-  }
-  __syncthreads();
-  if (t < nv) {
-    const double* vals = reinterpret_cast<const double*>(mine + P2P_FLAG_BYTES) + (size_t)b * SLA_MAX_WORLD * P2P_MAX_NV;
-    double a = 0.0;
-    for (int r = 0; r < world; ++r) a += ld_relaxed_sys_f64(vals + (size_t)r * P2P_MAX_NV + t);   // rank order: the same bits on every rank
-    sum[t] = a;
-  }
-  __syncthreads();
-  if (t == 0) finalize_scalars(fin, dst, scal, sum, nv);
+  p2p_allreduce_block(a, sum, nv);
+  if (threadIdx.x == 0) finalize_scalars(fin, dst, scal, sum, nv);
 }
 
 // ---- x exchange ------------------------------------------------------------------------------------------
@@ -156,6 +109,45 @@ p2p_push_kernel(const p2p_item* __restrict__ items, int nitems, char* const* __r
   const int t = threadIdx.x;
   if (t < world && t != rank) st_release_sys_u64(reinterpret_cast<unsigned long long*>(peer[t]) + rank, seq);
   if (t < world && t != rank) wait_flag(reinterpret_cast<const unsigned long long*>(peer[rank]) + t, seq, err);
+}
+
+// mode 3, the LL halo exchange — ONE kernel per exchange, no fence, no flag, no rendezvous:
+//   CTAs [0, nsend)        store the planned pieces of the local slice into the destinations' halo buffers as 16-byte entries
+//                          {lo32, tag, hi32, tag}: each 8-byte half carries its own tag, so a reader that sees both tags has the
+//                          whole double (8-byte stores are single-copy atomic over NVLink — NCCL's LL protocol, for fp64);
+//   CTAs [nsend, nsend+nrecv) poll this rank's halo buffer until the entries of the CURRENT tag are there and unpack them
+//                          into the gathered-x buffer the (#>) kernel reads (plain doubles, global column index).
+// Every rank stores before it polls, so the kernel cannot deadlock; the cost on the critical path is one launch plus one
+// NVLink store latency.  Buffers are double-buffered by tag parity; the plan must be symmetric (dist.py: halo_eligible), which
+// bounds a sender to one exchange ahead of any rank that still reads the other buffer.
+__global__ void __launch_bounds__(P2P_PUSH_THREADS)
+p2p_halo_ll_kernel(const p2p_item* __restrict__ items, int nsend, int nrecv, char* const* __restrict__ peer, size_t buf_off,
+                   const double* __restrict__ x_local, double* __restrict__ xfull, int rank, unsigned tag, int* err) {
+  const int b = (int)blockIdx.x;
+  if (b >= nsend + nrecv) return;
+  const p2p_item it = items[b];
+  if (b < nsend) {
+    uint4* dst = reinterpret_cast<uint4*>(peer[it.peer] + buf_off) + it.goff;
+    const double* src = x_local + it.src;
+    for (int i = threadIdx.x; i < it.len; i += P2P_PUSH_THREADS) {
+      const double v = src[i];
+      const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+    }
+    return;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(peer[rank] + buf_off) + it.src;
+  double* dst = xfull + it.goff;
+  const long long t0 = clock64();
+  for (int i = threadIdx.x; i < it.len; i += P2P_PUSH_THREADS) {
+    uint4 v;
+    for (;;) {
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+      if (v.y == tag && v.w == tag) break;
+      if (clock64() - t0 > P2P_TIMEOUT_CYCLES) { atomicExch(err, 1); break; }
+    }
+    dst[i] = __hiloint2double((int)v.z, (int)v.x);
+  }
 }
 
 // mode 2: the flag that follows a copy-engine block on the comm stream, and the per-source wait before a panel kernel
@@ -248,11 +240,25 @@ bool sla_p2p_active(const sla_ctx* c) { return c->p2p && c->p2p->enabled; }
 
 // all-reduce of scal[src .. src+nv) over the ranks followed by the scalar post-processing `fin` (nv <= P2P_MAX_NV = 32)
 sla_status sla_p2p_allreduce(sla_ctx* c, int nv, int src, int fin, int dst) {
-  sla_p2p* P = c->p2p;
-  P->seq++;
-  p2p_allreduce_kernel<<<1, P2P_AR_THREADS, 0, c->stream>>>(P->d_peer, c->rank, c->world, P->seq, nv, src, fin, dst, c->scal, P->d_err);
+  p2p_allreduce_kernel<<<1, P2P_AR_THREADS, 0, c->stream>>>(sla_p2p_next(c), nv, src, fin, dst, c->scal);
   SLA_LAUNCH_CHECK(c);
   return SLA_OK;
+}
+
+// arguments of the next all-reduce over the context window (inline in the reducing kernel, or the stand-alone kernel):
+// one sequence number per reduction, drawn in issue order — identical on every rank because the call sequence is
+sla_p2p_args sla_p2p_next(sla_ctx* c) {
+  sla_p2p* P = c->p2p;
+  sla_p2p_args a;
+  a.peer = P->d_peer; a.err = P->d_err; a.seq = ++P->seq; a.rank = c->rank; a.world = c->world;
+  return a;
+}
+
+// the last CTA of every reducing kernel completes the all-reduce itself (default); SLA_P2P_INLINE=0: separate one-CTA kernel
+bool sla_p2p_inline(const sla_ctx* c) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SLA_P2P_INLINE"); on = e ? atoi(e) != 0 : 1; }
+  return on && sla_p2p_active(c);
 }
 
 // reports a timed-out wait (called at synchronisation points)
@@ -276,6 +282,30 @@ void sla_p2p_free(sla_ctx* c) {
 
 // ---- matrix windows --------------------------------------------------------------------------------------------
 
+// LL halo plan: base[s] belongs to segment s of the plan given to sla_csr_set_dist — for a receive segment the compact
+// offset of its first entry in this rank's halo buffer, for a send segment the offset in the destination's buffer (the
+// host derives both from the global table of column ranges, dist.py).  Call before sla_csr_p2p_export.
+extern "C" sla_status sla_csr_set_halo(sla_ctx* c, sla_csr* A, int nseg, const int64_t* base) {
+  if (!c || !A || !A->dist || nseg < 0 || (nseg > 0 && !base)) return SLA_ERR_INVALID;
+  sla_dist_info* d = A->dist;
+  if (nseg != d->nseg) return sla_fail(c, SLA_ERR_INVALID, "set_halo: one base per exchange segment expected");
+  if (d->xwin) return sla_fail(c, SLA_ERR_INVALID, "set_halo: the exchange window already exists");
+  int nrecv = 0;
+  int64_t total = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (base[s] < 0) return sla_fail(c, SLA_ERR_INVALID, "set_halo: negative offset");
+    if (d->seg[s].dir == 0) { ++nrecv; if (base[s] + d->seg[s].count > total) total = base[s] + d->seg[s].count; }
+  }
+  (void)nrecv;
+  if (total >= (int64_t)1 << 31) return sla_fail(c, SLA_ERR_INVALID, "set_halo: halo too large");
+  delete[] d->seg_base;
+  d->seg_base = new (std::nothrow) int64_t[nseg > 0 ? nseg : 1];
+  if (!d->seg_base) return sla_fail(c, SLA_ERR_ALLOC, "set_halo alloc");
+  for (int s = 0; s < nseg; ++s) d->seg_base[s] = base[s];
+  d->halo_total = total;
+  return SLA_OK;
+}
+
 extern "C" sla_status sla_csr_p2p_export(sla_ctx* c, sla_csr* A, void* handle64) {
   if (!c || !A || !handle64) return SLA_ERR_INVALID;
   memset(handle64, 0, 64);
@@ -287,7 +317,8 @@ extern "C" sla_status sla_csr_p2p_export(sla_ctx* c, sla_csr* A, void* handle64)
     if (!X) return sla_fail(c, SLA_ERR_ALLOC, "p2p alloc");
     memset(X, 0, sizeof(*X));
     d->xwin = X;
-    X->buf_bytes = (sizeof(double) * (size_t)(A->n + 2) + 255) & ~(size_t)255;
+    X->ll = d->seg_base != nullptr;
+    X->buf_bytes = X->ll ? ((16 * (size_t)(d->halo_total + 1) + 255) & ~(size_t)255) : ((sizeof(double) * (size_t)(A->n + 2) + 255) & ~(size_t)255);
     const size_t bytes = P2P_FLAG_BYTES + 2 * X->buf_bytes;
     SLA_CUDA(c, cudaMalloc(&X->win, bytes));
     SLA_CUDA(c, cudaMemsetAsync(X->win, 0, bytes, c->stream));
@@ -295,10 +326,12 @@ extern "C" sla_status sla_csr_p2p_export(sla_ctx* c, sla_csr* A, void* handle64)
     SLA_CUDA(c, cudaMalloc(&X->d_ticket, sizeof(unsigned int)));
     SLA_CUDA(c, cudaMemsetAsync(X->d_ticket, 0, sizeof(unsigned int), c->stream));
     // work items: every send segment cut into P2P_ITEM_LEN pieces (cuts at even offsets keep the 16-byte path)
-    int total = 0;
-    for (int s = 0; s < d->nseg; ++s)
-      if (d->seg[s].dir == 1) total += (int)((d->seg[s].count + P2P_ITEM_LEN - 1) / P2P_ITEM_LEN);
-    p2p_item* items = new (std::nothrow) p2p_item[total > 0 ? total : 1];
+    int total = 0, total_recv = 0;
+    for (int s = 0; s < d->nseg; ++s) {
+      const int pieces = (int)((d->seg[s].count + P2P_ITEM_LEN - 1) / P2P_ITEM_LEN);
+      if (d->seg[s].dir == 1) total += pieces; else if (X->ll) total_recv += pieces;
+    }
+    p2p_item* items = new (std::nothrow) p2p_item[total + total_recv > 0 ? total + total_recv : 1];
     if (!items) return sla_fail(c, SLA_ERR_ALLOC, "p2p alloc");
     int k = 0;
     for (int s = 0; s < d->nseg; ++s) {
@@ -307,14 +340,28 @@ extern "C" sla_status sla_csr_p2p_export(sla_ctx* c, sla_csr* A, void* handle64)
       for (int64_t o = 0; o < g.count; o += P2P_ITEM_LEN) {
         items[k].peer = g.peer;
         items[k].len = (int)(g.count - o < P2P_ITEM_LEN ? g.count - o : P2P_ITEM_LEN);
-        items[k].goff = g.goff + o;
+        items[k].goff = X->ll ? d->seg_base[s] + o : g.goff + o;      // LL: compact index in the destination's halo buffer
         items[k].src = g.goff + o - d->row0;
         ++k;
       }
     }
+    // LL windows: the unpack items follow — where a received piece sits in this rank's halo buffer and where it goes in xfull
+    for (int s = 0; s < d->nseg && X->ll; ++s) {
+      const sla_xseg& g = d->seg[s];
+      if (g.dir != 0) continue;
+      for (int64_t o = 0; o < g.count; o += P2P_ITEM_LEN) {
+        items[k].peer = -1;
+        items[k].len = (int)(g.count - o < P2P_ITEM_LEN ? g.count - o : P2P_ITEM_LEN);
+        items[k].goff = g.goff + o;
+        items[k].src = d->seg_base[s] + o;
+        ++k;
+      }
+    }
     X->nitems = total;
-    cudaError_t e = cudaMalloc(&X->d_items, sizeof(p2p_item) * (size_t)(total > 0 ? total : 1));
-    if (e == cudaSuccess && total > 0) e = cudaMemcpyAsync(X->d_items, items, sizeof(p2p_item) * (size_t)total, cudaMemcpyHostToDevice, c->stream);
+    X->nrecv = total_recv;
+    const int all = total + total_recv;
+    cudaError_t e = cudaMalloc(&X->d_items, sizeof(p2p_item) * (size_t)(all > 0 ? all : 1));
+    if (e == cudaSuccess && all > 0) e = cudaMemcpyAsync(X->d_items, items, sizeof(p2p_item) * (size_t)all, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     delete[] items;
     SLA_CUDA(c, e);
@@ -340,26 +387,40 @@ extern "C" sla_status sla_csr_p2p_enable(sla_ctx* c, sla_csr* A, int on) {
   if (!d->xwin) return on ? sla_fail(c, SLA_ERR_INVALID, "p2p: no matrix window exported") : SLA_OK;
   if (on && !d->xwin->peer[c->rank]) return sla_fail(c, SLA_ERR_INVALID, "p2p: matrix windows not attached");
   if (on && !sla_p2p_active(c)) return sla_fail(c, SLA_ERR_INVALID, "p2p: the context-level switch is off");
-  int mode = on ? 1 : 0;
-  if (on == 2) {
-    // arrival-order mode needs one column panel per source rank: equal blocks in rank order, panel width = block size.
-    // The test only looks at global quantities, so every rank takes the same branch.
+  if (on && d->xwin->ll && on != 3) return sla_fail(c, SLA_ERR_INVALID, "p2p: this window was built for the LL halo exchange (mode 3)");
+  if (on == 3 && !d->xwin->ll) return sla_fail(c, SLA_ERR_INVALID, "p2p: mode 3 needs sla_csr_set_halo before sla_csr_p2p_export");
+  int mode = on == 3 ? 3 : on ? 1 : 0;
+  if ((on == 2 || on == 4) && d->dense_equal && c->comm_stream != nullptr) {
+    // Copy-engine all-gather.  Arrival-order consumption (mode 2) needs one column panel per source rank — equal blocks in
+    // rank order, panel width = block size — and pays one extra pass over y and row_ptr per panel, so it is chosen only when
+    // x would not stay L2-resident anyway (8 n above the panel threshold: the single-GPU plan panelises such matrices too);
+    // otherwise the blocks are waited for as a whole and the matrix keeps its own plan (mode 4).  The tests only look at
+    // global quantities (n, world), so every rank takes the same branch.
     const int W = c->world;
     const bool eligible = A->n % W == 0 && A->m == A->n / W && d->row0 == (int64_t)c->rank * A->m && A->m % 16 == 0 && A->m > 0 &&
-                          W <= SLA_MAX_PANELS && c->comm_stream != nullptr;
-    if (eligible) {
+                          W <= SLA_MAX_PANELS;
+    const bool big_x = (uint64_t)A->n * 8u > (56u << 20);
+    mode = 4;
+    if (on == 2 && eligible && (big_x || getenv("SLA_P2P_ARRIVAL_ALWAYS"))) {
       SLA_TRY(sla_csr_force_panels(c, A, W));
       if (A->npanels == W && A->panel_width == A->m) mode = 2;
     }
   }
+  const bool was_in_window = d->xwin->enabled && !d->xwin->ll;
   d->xwin->enabled = on ? 1 : 0;
   d->xwin->mode = mode;
-  if (on) {
+  SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (on && !d->xwin->ll) {
     // the kernels now read the remote entries from the window: the private gathered-x buffer is not needed
-    SLA_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(d->xfull);
+    if (!was_in_window) cudaFree(d->xfull);
     d->xfull = reinterpret_cast<double*>(d->xwin->win + P2P_FLAG_BYTES);
     d->allgather = 0; d->pipelined = 0;
+  } else if (!on && was_in_window) {
+    // back to NCCL: a private gathered-x buffer again, and the collective all-gather decision as installed
+    d->xfull = nullptr;
+    SLA_CUDA(c, cudaMalloc(&d->xfull, sizeof(double) * (size_t)((A->n + 2) & ~(int64_t)1)));
+    SLA_CUDA(c, cudaMemsetAsync(d->xfull, 0, sizeof(double) * (size_t)A->n, c->stream));
+    d->allgather = d->dense_equal;
   }
   return SLA_OK;
 }
@@ -400,7 +461,8 @@ sla_status sla_p2p_arrival_end(sla_ctx* c) {
 // mode 2, step 2 (compute stream): block of rank `src` has arrived in the current buffer
 sla_status sla_p2p_arrival_wait(sla_ctx* c, const sla_csr* A, int src) {
   sla_xwin* X = A->dist->xwin;
-  p2p_wait_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const unsigned long long*>(X->win), 1u << src, X->seq, c->p2p->d_err);
+  const unsigned mask = src >= 0 ? 1u << src : (((1u << c->world) - 1u) & ~(1u << c->rank));   // src < 0: every other rank
+  p2p_wait_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const unsigned long long*>(X->win), mask, X->seq, c->p2p->d_err);
   SLA_LAUNCH_CHECK(c);
   return SLA_OK;
 }
@@ -412,6 +474,19 @@ sla_status sla_p2p_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_loca
   sla_xwin* X = d->xwin;
   X->seq++;
   const size_t off = P2P_FLAG_BYTES + (size_t)(X->seq & 1ull) * X->buf_bytes;
+  if (X->mode == 3) {
+    if (X->nitems + X->nrecv > 0) {
+      p2p_halo_ll_kernel<<<X->nitems + X->nrecv, P2P_PUSH_THREADS, 0, c->stream>>>(X->d_items, X->nitems, X->nrecv, X->d_peer, off, x_local,
+                                                                                   d->xfull, c->rank, (unsigned)X->seq, c->p2p->d_err);
+      SLA_LAUNCH_CHECK(c);
+    }
+    return SLA_OK;
+  }
+  if (X->mode == 2 || X->mode == 4) {           // (#>) drives these itself; other callers get the whole gather
+    SLA_TRY(sla_p2p_arrival_begin(c, A, x_local));
+    SLA_TRY(sla_p2p_arrival_wait(c, A, -1));
+    return sla_p2p_arrival_end(c);
+  }
   const int grid = X->nitems > 0 ? X->nitems : 1;
   p2p_push_kernel<<<grid, P2P_PUSH_THREADS, 0, c->stream>>>(X->d_items, X->nitems, X->d_peer, off, x_local, c->rank, c->world,
                                                           X->seq, X->d_ticket, c->p2p->d_err);
@@ -431,7 +506,7 @@ void sla_xwin_free(sla_csr* A) {
   if (c && c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c) close_peers(c, X->peer);
   cudaFree(X->d_peer); cudaFree(X->d_items); cudaFree(X->d_ticket);
-  if (X->enabled) d->xfull = nullptr;            // it pointed into the window
+  if (d->xfull && (char*)d->xfull >= X->win && (char*)d->xfull < X->win + P2P_FLAG_BYTES + 2 * X->buf_bytes) d->xfull = nullptr;   // it pointed into the window
   if (c && c->n_parked < SLA_MAX_PARKED) c->parked[c->n_parked++] = X->win;   // else: leaked until process exit
   delete X;
   d->xwin = nullptr;

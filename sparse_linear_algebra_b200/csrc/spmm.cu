@@ -104,7 +104,8 @@ extern "C" sla_status sla_dense_create(sla_ctx* c, int64_t rows, int64_t cols, i
   if (!d) return sla_fail(c, SLA_ERR_ALLOC, "dense alloc");
   d->ctx = c; d->rows = rows; d->cols = cols; d->ld = cols; d->dtype = dtype; d->rowmajor = 1; d->d = nullptr;
   const size_t bytes = (size_t)rows * (size_t)cols * elt_bytes(dtype);
-  if (cudaMalloc((void**)&d->d, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); delete d; return sla_fail(c, SLA_ERR_ALLOC, "cudaMalloc failed for a dense block"); }
+  d->bytes = bytes < 16 ? 16 : bytes;
+  if (sla_pool_alloc(c, (void**)&d->d, d->bytes) != cudaSuccess) { cudaGetLastError(); delete d; return sla_fail(c, SLA_ERR_ALLOC, "cudaMalloc failed for a dense block"); }
   cudaMemsetAsync(d->d, 0, bytes, c->stream);
   *out = d;
   return SLA_OK;

@@ -80,6 +80,18 @@ __device__ __forceinline__ double ld_keep_double_na(const double* p, uint64_t po
 
 __device__ __forceinline__ int skew(int k, int a) { return k + (k >> a); }   // a = 31: no skew
 
+// A row block of a multi-GPU matrix carries GLOBAL column indices: columns inside [col0, col0 + ncl) are read from the local
+// slice x, every other column from the gathered-x buffer xr (indexed by global column), which the exchange that precedes the
+// kernel has filled — an all-gather, a peer-memory push, copy-engine blocks consumed in arrival order, or the LL halo
+// exchange (p2p.cu modes 1-4, dist.cu for NCCL).
+// x_j for the out-of-tile paths (row tails, long rows)
+template <int DIST>
+__device__ __forceinline__ double fetch_x(const double* __restrict__ x, int c, const SpmvDist& dx) {
+  if (DIST == 0) return x[c];
+  if ((unsigned)(c - dx.col0) < (unsigned)dx.ncl) return x[c - dx.col0];
+  return dx.xr[c];
+}
+
 template <int EPI>
 __device__ __forceinline__ void row_epilogue(int r, double acc, double* y, const double* __restrict__ u0,
                                              double& e0, double& e1) {
@@ -93,17 +105,46 @@ __device__ __forceinline__ void row_epilogue(int r, double acc, double* y, const
   if (EPI == EPI_DOT2_YY) e1 += acc * acc;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
 // ACC = false: row sums start from 0.0.  ACC = true: they continue from yin[r] (a later column panel).
-// DIST = true (row block of a multi-GPU matrix, GLOBAL column indices): columns inside [col0, col0 + ncl) are
-// read from the local slice x, every other column from the exchanged buffer xr.
-template <int TILE, int EPI, bool ACC, bool DIST>
+// DIST > 0: row block of a multi-GPU matrix, see SpmvDist.
+// STAGE = 0: every thread loads its 8 (col, val) pairs straight into registers (lane-contiguous LDG).
+// STAGE = 1: the tile's 12 KB arrive through TWO BULK COPIES (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) issued by
+//            thread 0 at CTA start; the threads then read their pairs from shared memory.  The point is the L1TEX request port:
+//            on random columns the kernel is bound by ~0.95 requests per SM-cycle (profiles/r02_gather_paths.jsonl), 9 % of which
+//            were the stream's own line requests; the bulk-copy engine does not use that port.  The product buffer overlays the
+//            staging area (every thread has its pairs in registers before the first product is written), so shared memory per
+//            CTA stays at 12 KB and occupancy at 16 CTAs per SM — unlike the persistent 3-stage ring of spmv_tma_kernel below.
+template <int TILE, int EPI, bool ACC, int DIST, int STAGE>
 __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val,
                  const double* __restrict__ x, const double* yin, double* y, const int* __restrict__ tile_row,
-                 const double* __restrict__ u0, double* partials, unsigned int* counter, double* scal,
-                 int fin, int dst, int hints, const double* __restrict__ xr, int col0, int ncl, int tile0) {
+                 const double* __restrict__ u0, double* partials, int hints, const SpmvDist dx, int tile0) {
   constexpr int PER = TILE / SPMV_THREADS;                // entries per thread, lane-contiguous
-  __shared__ double prod[TILE + TILE / 8];              // keep CTA smem small: the L1 left over holds the in-flight gathers
+  // keep CTA smem small: the L1 left over holds the in-flight gathers.  STAGE 1: [val 8 KB | col 4 KB], products overlay it.
+  __shared__ __align__(128) double prod_store[STAGE ? (TILE * 12) / 8 : TILE + TILE / 8];
+  __shared__ uint64_t stage_bar;
+  double* prod = prod_store;
   __shared__ double red[2 * 32];
   __shared__ int long_rows[SLA_LONG_CAP];
   __shared__ int n_long;
@@ -115,6 +156,17 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
   const int nrows = row_hi - row_lo;
   const int sk = hints >> 8;                              // skew shift a
   if (tid == 0) n_long = 0;
+  if (STAGE && nrows > 0) {
+    if (tid == 0) {
+      const uint64_t pol = (hints & 1) ? policy_evict_first() : policy_evict_normal();
+      mbar_init(&stage_bar, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the init must be visible to the async proxy
+      mbar_expect_tx(&stage_bar, TILE * 12);
+      bulk_g2s(prod_store, val + base, TILE * 8, &stage_bar, pol);
+      bulk_g2s(reinterpret_cast<unsigned char*>(prod_store) + TILE * 8, col + base, TILE * 4, &stage_bar, pol);
+    }
+    __syncthreads();                                      // nobody waits on the barrier before it is initialised
+  }
 
   // ---- phase 1: stream the tile, gather x, write products --------------------------------------
   if (nrows > 0) {
@@ -122,19 +174,31 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
     const uint64_t pol_keep = (hints & 2) ? policy_evict_last() : policy_evict_normal();
     int c[PER];
     double v[PER];
+    if (STAGE) {
+      mbar_wait(&stage_bar, 0);
+      const int* sc = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(prod_store) + TILE * 8);
 #pragma unroll
-    for (int it = 0; it < PER; ++it) {
-      const int k = it * SPMV_THREADS + tid;
-      c[it] = ld_stream_int(col + base + k, pol_stream);
-      v[it] = ld_stream_double(val + base + k, pol_stream);
+      for (int it = 0; it < PER; ++it) {
+        const int k = it * SPMV_THREADS + tid;
+        c[it] = sc[k];
+        v[it] = prod_store[k];
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < PER; ++it) {
+        const int k = it * SPMV_THREADS + tid;
+        c[it] = ld_stream_int(col + base + k, pol_stream);
+        v[it] = ld_stream_double(val + base + k, pol_stream);
+      }
     }
     double xv[PER];
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
       const double* src = x + c[it];
-      if (DIST) src = (unsigned)(c[it] - col0) < (unsigned)ncl ? x + (c[it] - col0) : xr + c[it];
+      if (DIST == 1) src = (unsigned)(c[it] - dx.col0) < (unsigned)dx.ncl ? x + (c[it] - dx.col0) : dx.xr + c[it];
       xv[it] = (hints & 4) ? ld_keep_double_na(src, pol_keep) : ld_keep_double(src, pol_keep);
     }
+    if (STAGE) __syncthreads();                             // every thread holds its pairs: the staging area becomes the product buffer
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
       const int k = it * SPMV_THREADS + tid;
@@ -160,7 +224,7 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
     for (int k = (ks > TILE ? ks : TILE); k < ke; ++k) {     // tail beyond the tile (last owned row only)
       const int g = base + k;
       const int cg = col[g];
-      const double xg = DIST ? ((unsigned)(cg - col0) < (unsigned)ncl ? x[cg - col0] : xr[cg]) : x[cg];
+      const double xg = fetch_x<DIST>(x, cg, dx);
       acc = __dadd_rn(acc, __dmul_rn(val[g], xg));
     }
     row_epilogue<EPI>(r, acc, y, u0, e0, e1);
@@ -181,7 +245,7 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
         else {
           const int g = base + k;
           const int cg = col[g];
-          const double xg = DIST ? ((unsigned)(cg - col0) < (unsigned)ncl ? x[cg - col0] : xr[cg]) : x[cg];
+          const double xg = fetch_x<DIST>(x, cg, dx);
           t = __dmul_rn(val[g], xg);
         }
         acc += t;
@@ -204,7 +268,6 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
       partials[blockIdx.x] = sums[0];
       partials[(size_t)gridDim.x + blockIdx.x] = sums[1];
     }
-    (void)counter; (void)scal; (void)fin; (void)dst;
   }
 }
 
@@ -216,33 +279,11 @@ spmv_tile_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, c
 // Arithmetic, ownership rule, epilogues and bit-exactness are those of spmv_tile_kernel.
 #define SPMV_STAGES 3
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-
-template <int TILE, int EPI, bool ACC, bool DIST>
+template <int TILE, int EPI, bool ACC, int DIST>
 __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_tma_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val,
                 const double* __restrict__ x, const double* yin, double* y, const int* __restrict__ tile_row,
-                const double* __restrict__ u0, double* partials, int ntiles, int hints,
-                const double* __restrict__ xr, int col0, int ncl) {
+                const double* __restrict__ u0, double* partials, int ntiles, int hints, const SpmvDist dx) {
   constexpr int PER = TILE / SPMV_THREADS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sval = reinterpret_cast<double*>(smem_raw);                                   // STAGES x TILE doubles
@@ -300,7 +341,7 @@ spmv_tma_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, co
 #pragma unroll
       for (int q = 0; q < PER; ++q) {
         const double* src = x + c[q];
-        if (DIST) src = (unsigned)(c[q] - col0) < (unsigned)ncl ? x + (c[q] - col0) : xr + c[q];
+        if (DIST == 1) src = (unsigned)(c[q] - dx.col0) < (unsigned)dx.ncl ? x + (c[q] - dx.col0) : dx.xr + c[q];
         xv[q] = (hints & 4) ? ld_keep_double_na(src, pol_keep) : ld_keep_double(src, pol_keep);
       }
 #pragma unroll
@@ -338,7 +379,7 @@ spmv_tma_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, co
       for (int k = (ks > TILE ? ks : TILE); k < ke; ++k) {
         const int g = base + k;
         const int cg = col[g];
-        const double xg = DIST ? ((unsigned)(cg - col0) < (unsigned)ncl ? x[cg - col0] : xr[cg]) : x[cg];
+        const double xg = fetch_x<DIST>(x, cg, dx);
         acc = __dadd_rn(acc, __dmul_rn(val[g], xg));
       }
       row_epilogue<EPI>(r, acc, y, u0, e0, e1);
@@ -357,7 +398,7 @@ spmv_tma_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, co
           else {
             const int g = base + k;
             const int cg = col[g];
-            const double xg = DIST ? ((unsigned)(cg - col0) < (unsigned)ncl ? x[cg - col0] : xr[cg]) : x[cg];
+            const double xg = fetch_x<DIST>(x, cg, dx);
             t = __dmul_rn(val[g], xg);
           }
           acc += t;
@@ -612,7 +653,7 @@ sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P) {
 #define PRED_THREADS 256
 __global__ void __launch_bounds__(PRED_THREADS)
 partials_reduce_kernel(const double* __restrict__ partials, int nblk, double* partials2, unsigned int* counter,
-                       double* scal, int fin, int dst) {
+                       double* scal, int fin, int dst, sla_p2p_args pa) {
   __shared__ double red[2 * 32];
   const int per = (nblk + gridDim.x - 1) / gridDim.x;
   const int lo = blockIdx.x * per, hi = min(nblk, lo + per);
@@ -623,7 +664,7 @@ partials_reduce_kernel(const double* __restrict__ partials, int nblk, double* pa
   }
   block_sum<2>(acc, red);
   __syncthreads();
-  grid_reduce_finish<2>(acc, partials2, counter, scal, fin, dst, red);
+  grid_reduce_finish<2>(acc, partials2, counter, scal, fin, dst, red, pa);
 }
 
 // everything one launch needs besides the epilogue selection
@@ -632,17 +673,17 @@ struct SpmvArgs {
   int ntiles, skew_a, hints;
   const double *x, *yin; double* y; const double* u0;
   int fin, dst;
-  const double* xr; int col0, ncl;     // DIST only
+  SpmvDist dx;                         // DIST > 0 only
   int tile0;                           // first tile of this launch (row-chunked launches of sla_spmv_host)
 };
 
-template <int EPI, bool ACC, bool DIST>
+template <int EPI, bool ACC, int DIST>
 static sla_status launch_one(sla_ctx* c, const SpmvArgs& a) {
   static int carve_set = 0;
   if (!carve_set) {
     carve_set = 1;
     if (const char* e = getenv("SLA_SPMV_CARVEOUT"))
-      cudaFuncSetAttribute(spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+      cudaFuncSetAttribute(spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
   }
   int nblk = a.ntiles;
   if (c->spmv_tma) {
@@ -654,27 +695,32 @@ static sla_status launch_one(sla_ctx* c, const SpmvArgs& a) {
       SLA_CUDA(c, cudaFuncSetAttribute(spmv_tma_kernel<SLA_SPMV_TILE, EPI, ACC, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     nblk = a.ntiles < SLA_NUM_SMS * c->spmv_tma ? a.ntiles : SLA_NUM_SMS * c->spmv_tma;
+    if (a.tile0 != 0) return sla_fail(c, SLA_ERR_INVALID, "spmv: the TMA-staged variant does not take row-chunked launches");
     spmv_tma_kernel<SLA_SPMV_TILE, EPI, ACC, DIST><<<nblk, SPMV_THREADS, smem, c->stream>>>(
         a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, a.ntiles,
-        (a.hints & 0xff) | (a.skew_a << 8), a.xr, a.col0, a.ncl);
+        (a.hints & 0xff) | (a.skew_a << 8), a.dx);
   } else {
-    spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST><<<a.ntiles, SPMV_THREADS, 0, c->stream>>>(
-        a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, c->counter, c->scal,
-        EPI != EPI_NONE ? fin_for(c, a.fin) : a.fin, a.dst, (a.hints & 0xff) | (a.skew_a << 8), a.xr, a.col0, a.ncl, a.tile0);
+    if (c->spmv_bulk && DIST == 0)
+      spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, 0, 1><<<a.ntiles, SPMV_THREADS, 0, c->stream>>>(
+          a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, (a.hints & 0xff) | (a.skew_a << 8), a.dx, a.tile0);
+    else
+      spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST, 0><<<a.ntiles, SPMV_THREADS, 0, c->stream>>>(
+          a.row_ptr, a.col, a.val, a.x, a.yin, a.y, a.tile_row, a.u0, c->partials, (a.hints & 0xff) | (a.skew_a << 8), a.dx, a.tile0);
   }
   SLA_LAUNCH_CHECK(c);
   if (EPI != EPI_NONE) {
     int g = nblk / 2048;
     g = g < 1 ? 1 : (g > 128 ? 128 : g);
+    const sla_red_plan rp = sla_red_begin(c, a.fin, 2);
     partials_reduce_kernel<<<g, PRED_THREADS, 0, c->stream>>>(c->partials, nblk, c->partials + 2 * (size_t)SLA_MAX_PARTIALS, c->counter,
-                                                             c->scal, fin_for(c, a.fin), a.dst);
+                                                             c->scal, rp.fin, a.dst, rp.pa);
     SLA_LAUNCH_CHECK(c);
-    SLA_TRY(sla_dist_finish_reduction(c, 2, a.fin, a.dst));
+    SLA_TRY(sla_red_end(c, rp, 2, a.fin, a.dst));
   }
   return SLA_OK;
 }
 
-template <bool ACC, bool DIST>
+template <bool ACC, int DIST>
 static sla_status launch_epi(sla_ctx* c, int epi, const SpmvArgs& a) {
   switch (epi) {
     case EPI_NONE:    return launch_one<EPI_NONE, ACC, DIST>(c, a);
@@ -685,9 +731,15 @@ static sla_status launch_epi(sla_ctx* c, int epi, const SpmvArgs& a) {
   return sla_fail(c, SLA_ERR_INVALID, "spmv: unknown epilogue");
 }
 
-static sla_status launch_any(sla_ctx* c, int epi, bool acc, bool dist, const SpmvArgs& a) {
-  if (dist) return acc ? launch_epi<true, true>(c, epi, a) : launch_epi<false, true>(c, epi, a);
-  return acc ? launch_epi<true, false>(c, epi, a) : launch_epi<false, false>(c, epi, a);
+static sla_status launch_any(sla_ctx* c, int epi, bool acc, int dist, const SpmvArgs& a) {
+  if (dist == 1) return acc ? launch_epi<true, 1>(c, epi, a) : launch_epi<false, 1>(c, epi, a);
+  return acc ? launch_epi<true, 0>(c, epi, a) : launch_epi<false, 0>(c, epi, a);
+}
+
+static void dist_args(const sla_csr* A, SpmvDist* dx) {
+  memset(dx, 0, sizeof(*dx));
+  if (!A->dist) return;
+  dx->xr = A->dist->xfull; dx->col0 = (int)A->dist->row0; dx->ncl = (int)A->m;
 }
 
 // Row-partitioned (#>) in ARRIVAL order (p2p.cu mode 2, SLA_P2P_X=2; not yet run on hardware): one column panel per
@@ -696,10 +748,11 @@ static sla_status launch_any(sla_ctx* c, int epi, bool acc, bool dist, const Spm
 // column order: a valid summation of the same products (SURVEY.md §8(d) bound), not the bit-exact ascending fold.
 static sla_status spmv_launch_arrival(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi, const double* u0, int fin, int dst) {
   const int W = c->world;
-  SLA_TRY(sla_p2p_arrival_begin(c, A, x));
+  const bool skip = c->skip_exchange != 0;                // diagnostic: kernels only
+  if (!skip) SLA_TRY(sla_p2p_arrival_begin(c, A, x));
   SpmvArgs a;
   a.hints = A->hints; a.x = x; a.u0 = u0; a.fin = fin; a.dst = dst;
-  a.xr = A->dist->xfull; a.col0 = (int)A->dist->row0; a.ncl = (int)A->m; a.tile0 = 0;
+  dist_args(A, &a.dx); a.tile0 = 0;
   double* ybuf = y;
   if (epi == EPI_RESNORM) {
     if (!c->scratch_r || c->scratch_r->n != A->m) {
@@ -710,14 +763,14 @@ static sla_status spmv_launch_arrival(sla_ctx* c, const sla_csr* A, const double
   }
   for (int k = 0; k < W; ++k) {
     const int q = (c->rank - k + W) % W;                 // rank r-1 sends to me first, r-2 second, ...
-    if (k > 0) SLA_TRY(sla_p2p_arrival_wait(c, A, q));
+    if (k > 0 && !skip) SLA_TRY(sla_p2p_arrival_wait(c, A, q));
     const sla_panel& pn = A->panels[q];
     a.row_ptr = pn.row_ptr; a.col = pn.col; a.val = pn.val; a.tile_row = pn.tile_row;
     a.ntiles = pn.ntiles; a.skew_a = pn.skew_a;
     a.yin = k == 0 ? nullptr : ybuf; a.y = ybuf;
-    SLA_TRY(launch_any(c, k + 1 == W ? epi : EPI_NONE, k > 0, true, a));
+    SLA_TRY(launch_any(c, k + 1 == W ? epi : EPI_NONE, k > 0, 1, a));
   }
-  return sla_p2p_arrival_end(c);
+  return skip ? SLA_OK : sla_p2p_arrival_end(c);
 }
 
 // y = A x with an optional fused epilogue.  u1 is reserved (EPI_DOT2_YY uses y itself).
@@ -729,8 +782,14 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   const bool dist = A->dist != nullptr;
   if (dist && c->world > 1 && sla_xwin_mode(A) == 2 && A->npanels == c->world && A->m > 0)
     return spmv_launch_arrival(c, A, x, y, epi, u0, fin, dst);
+  // mode 4: the same copy-engine all-gather, waited for as a whole, then the matrix's own plan (no per-source panels)
+  const bool ce_gather = dist && c->world > 1 && sla_xwin_mode(A) == 4 && !c->skip_exchange;
+  if (ce_gather) {
+    SLA_TRY(sla_p2p_arrival_begin(c, A, x));
+    SLA_TRY(sla_p2p_arrival_wait(c, A, -1));
+  }
   // Dense multi-GPU plans are pipelined: the exchange of panel p+1 (comm stream) overlaps the kernel of panel p.
-  const bool pipelined = dist && A->dist->pipelined && A->npanels >= 2 && c->world > 1;
+  const bool pipelined = dist && A->dist->pipelined && A->npanels >= 2 && c->world > 1 && !c->skip_exchange;
   if (pipelined) {
     SLA_CUDA(c, cudaEventRecord(c->ev_x0, c->stream));                  // x is final, earlier readers of xfull are done
     SLA_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_x0, 0));
@@ -738,16 +797,20 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
       SLA_TRY(sla_dist_exchange_panel(c, A, x, p));
       SLA_CUDA(c, cudaEventRecord(c->ev_panel[p], c->comm_stream));
     }
-  } else if (dist) {
+  } else if (dist && !c->skip_exchange && !ce_gather) {
     SLA_TRY(sla_dist_exchange_x(c, A, x));                              // every rank takes part, even with no local rows
   }
   SpmvArgs a;
   a.row_ptr = A->row_ptr; a.col = A->col; a.val = A->val; a.tile_row = A->tile_row;
   a.ntiles = A->ntiles; a.skew_a = A->skew_a; a.hints = A->hints;
   a.x = x; a.yin = nullptr; a.y = y; a.u0 = u0; a.fin = fin; a.dst = dst;
-  a.xr = dist ? A->dist->xfull : nullptr; a.col0 = dist ? (int)A->dist->row0 : 0; a.ncl = dist ? (int)A->m : 0;
+  dist_args(A, &a.dx);                                                  // after the exchange: it may flip the double buffer
   a.tile0 = 0;
-  if (A->npanels < 2) return launch_any(c, epi, false, dist, a);
+  const int dmode = dist ? 1 : 0;
+  if (A->npanels < 2) {
+    SLA_TRY(launch_any(c, epi, false, dmode, a));
+    return ce_gather ? sla_p2p_arrival_end(c) : SLA_OK;
+  }
   // column panels in ascending order; the epilogue rides on the last pass
   double* ybuf = y;
   if (epi == EPI_RESNORM) {          // y is not an output of this mode: keep the partial sums in a scratch vector
@@ -769,13 +832,13 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
       if (last) {
         a.row_ptr = A->row_ptr; a.col = A->col; a.val = A->val; a.tile_row = A->tile_row; a.ntiles = A->ntiles; a.skew_a = A->skew_a;
         a.yin = nullptr;
-        SLA_TRY(launch_any(c, epi, false, dist, a));
+        SLA_TRY(launch_any(c, epi, false, dmode, a));
       }
       continue;
     }
-    SLA_TRY(launch_any(c, last ? epi : EPI_NONE, p > 0, dist, a));
+    SLA_TRY(launch_any(c, last ? epi : EPI_NONE, p > 0, dmode, a));
   }
-  return SLA_OK;
+  return ce_gather ? sla_p2p_arrival_end(c) : SLA_OK;
 }
 
 // ---- (#>) on host buffers, pipelined ------------------------------------------------------------------------
@@ -818,7 +881,7 @@ sla_status sla_spmv_host_pipelined(sla_ctx* c, const sla_csr* A, const double* x
   }
   // 2. passes
   SpmvArgs a;
-  a.hints = A->hints; a.x = dx; a.u0 = nullptr; a.fin = FIN_STORE; a.dst = S_TMP0; a.xr = nullptr; a.col0 = 0; a.ncl = 0;
+  a.hints = A->hints; a.x = dx; a.u0 = nullptr; a.fin = FIN_STORE; a.dst = S_TMP0; memset(&a.dx, 0, sizeof(a.dx));
   for (int p = 0; p < P; ++p) {
     const bool last = p + 1 == P;
     if (P > 1) {
@@ -829,11 +892,11 @@ sla_status sla_spmv_host_pipelined(sla_ctx* c, const sla_csr* A, const double* x
     }
     a.yin = p == 0 ? nullptr : dy; a.y = dy; a.tile0 = 0;
     SLA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[p], 0));
-    if (!last) { SLA_TRY(launch_any(c, EPI_NONE, p > 0, false, a)); continue; }
+    if (!last) { SLA_TRY(launch_any(c, EPI_NONE, p > 0, 0, a)); continue; }
     for (int q = 0; q < SLA_HOST_CHUNKS; ++q) {
       const int t0 = A->chunk_tile[q], t1 = A->chunk_tile[q + 1];
       const int r0 = A->chunk_row[q], r1 = q + 1 == SLA_HOST_CHUNKS ? (int)A->m : A->chunk_row[q + 1];
-      if (t1 > t0) { a.tile0 = t0; a.ntiles = t1 - t0; SLA_TRY(launch_any(c, EPI_NONE, p > 0, false, a)); }
+      if (t1 > t0) { a.tile0 = t0; a.ntiles = t1 - t0; SLA_TRY(launch_any(c, EPI_NONE, p > 0, 0, a)); }
       cudaEvent_t ev = c->ev_copy[SLA_MAX_PANELS + 1 + q];
       SLA_CUDA(c, cudaEventRecord(ev, c->stream));
       SLA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, ev, 0));

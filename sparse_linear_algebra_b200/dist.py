@@ -73,6 +73,7 @@ def densify_needs(starts, needs):
 
     live = [q for q in range(world) if needs[q][1] >= needs[q][0]]
     dense = bool(live) and all(2 * halo_volume(q) > n - (starts[q + 1] - starts[q]) for q in live)
+    densify_needs.last_dense = dense            # read by distribute(): a dense plan never takes the LL halo path
     if not dense:
         return list(needs), False
     equal = n % world == 0 and all(starts[p] == p * (n // world) for p in range(world + 1))
@@ -90,17 +91,68 @@ def p2p_wanted():
 
 
 def p2p_exchange_mode():
-    """Transport of the x exchange (SLA_P2P_X): 0 = NCCL (default), 1 = peer-memory push kernel, 2 = copy-engine
-    all-gather consumed in arrival order (dense equal-block plans; falls back to 1 otherwise; not yet run on hardware).
-    Measured on B200 (profiles/r01_bench_{p2p,nccl}_n{2,4}.json): the push kernel is 3 % faster than ncclAllGather at
-    2 GPUs but 7 % slower at 4 (cfg 2), and ~4 us slower per (#>) than NCCL's grouped send/recv on the Laplacian halos,
-    while the peer-memory all-reduce wins everywhere — hence NCCL stays the default for the exchange."""
+    """Transport of the x exchange (SLA_P2P_X), -1 = automatic (the default when the variable is unset or "auto"):
+        0  NCCL (all-gather for dense equal-block plans, grouped send/recv otherwise)
+        1  peer-memory push kernel + flag round trip (any plan)
+        2  copy-engine all-gather (dense equal-block plans): every rank's block travels on the copy engines in a staggered
+           order.  When x is too large to stay L2-resident (8 n > 56 MB: such matrices are column-panelised on one GPU too) the
+           (#>) consumes the blocks in ARRIVAL order, one column panel per source rank, the transfer of block k+1 hidden
+           behind the kernel of panel k — rows are then folded in rotated column order, within the fp64 bound of SURVEY.md
+           section 8(d) instead of bit-identical; smaller x: the blocks are waited for as a whole (reported as mode 4, bit-exact)
+        3  LL halo (symmetric halo plans): ONE kernel stores 16-byte tagged entries straight into the neighbours' halo
+           buffers and unpacks the entries arriving from them — no fence, no flag round trip, no rendezvous
+        4  copy-engine all-gather waited for as a whole (what 2 degrades to)
+    Automatic = 2 for dense equal-block plans, 3 for eligible halo plans, NCCL otherwise.  Must agree on every rank."""
     if not p2p_wanted():
         return 0
+    v = os.environ.get("SLA_P2P_X", "auto")
+    if v in ("", "auto"):
+        return -1
     try:
-        return max(0, min(2, int(os.environ.get("SLA_P2P_X", "0"))))
+        return max(0, min(4, int(v)))
     except ValueError:
-        return 0
+        return -1
+
+
+HALO_MAX_SEGS = 15         # neighbours per rank (SLA_MAX_WORLD - 1)
+
+
+def halo_eligible(starts, needs):
+    """Collective decision (global tables only): the LL halo exchange needs every rank's plan to be SYMMETRIC — it sends to
+    exactly the ranks it receives from, which is what makes the double-buffered halo buffers safe without a barrier (a
+    sender can only be one exchange ahead of a neighbour it also waits for)."""
+    world = len(starts) - 1
+    any_seg = False
+    for q in range(world):
+        segs = plan_exchange(q, starts, needs)
+        recv = sorted(p for d, p, _, _ in segs if d == 0)
+        send = sorted(p for d, p, _, _ in segs if d == 1)
+        if recv != send or len(recv) > HALO_MAX_SEGS:
+            return False
+        any_seg = any_seg or bool(segs)
+    return any_seg
+
+
+def halo_bases(rank, starts, needs):
+    """Compact halo indices of this rank's plan: for a receive segment the offset of its first entry in this rank's halo
+    buffer (segments packed in plan order), for a send segment its offset in the DESTINATION's buffer.  Both sides derive
+    the same numbers because both walk plan_exchange(q, ...) of the same global table.  Returns (bases, entries received)."""
+    world = len(starts) - 1
+    cache = {}
+
+    def recv_offsets(q):
+        if q not in cache:
+            off, table = 0, {}
+            for d, peer, _, cnt in plan_exchange(q, starts, needs):
+                if d == 0:
+                    table[peer] = off
+                    off += cnt
+            cache[q] = (table, off)
+        return cache[q]
+
+    mine, total = recv_offsets(rank)
+    bases = [mine[peer] if d == 0 else recv_offsets(peer)[0][rank] for d, peer, _, _ in plan_exchange(rank, starts, needs)]
+    return bases, total
 
 
 def _p2p_handshake(export, attach, enable):
@@ -174,14 +226,26 @@ def distribute(ctx, A, starts):
     needs = [None] * world
     dist.all_gather_object(needs, (lo.value, hi.value))
     needs, allgather = densify_needs(starts, needs)
+    dense = densify_needs.last_dense
     segs = plan_exchange(rank, starts, needs)
     _install_plan(ctx, A, starts[rank], segs, allgather)
     # the x exchange: peers store their pieces straight into this rank's window (csrc/p2p.cu)
     A.dist_p2p = False
     A.dist_p2p_mode = 0
     mode = p2p_exchange_mode()
+    halo_ok = not dense and halo_eligible(starts, needs)
+    if mode == -1:
+        mode = 2 if allgather else (3 if halo_ok else 0)
+    elif mode == 3 and not halo_ok:
+        mode = 0
+    elif mode in (2, 4) and not allgather:
+        mode = 1
     if getattr(ctx, "p2p", False) and mode:
         lib = ctx.lib
+        if mode == 3:
+            bases, _ = halo_bases(rank, starts, needs)
+            arr = (C.c_int64 * max(len(bases), 1))(*bases)
+            ctx.check(lib.sla_csr_set_halo(ctx.h, A.h, len(bases), arr))
         A.dist_p2p = _p2p_handshake(lambda buf: lib.sla_csr_p2p_export(ctx.h, A.h, buf),
                                     lambda blob: lib.sla_csr_p2p_attach(ctx.h, A.h, blob),
                                     lambda on: ctx.check(lib.sla_csr_p2p_enable(ctx.h, A.h, mode if on else 0)))

@@ -89,6 +89,9 @@ class Context:
     def sync(self):
         self.check(self.lib.sla_sync(self.h))
 
+    def set_option(self, name, value):
+        self.check(self.lib.sla_set_option(self.h, name.encode(), int(value)))
+
     @property
     def launches(self):
         return self.lib.sla_launch_count(self.h)
@@ -288,6 +291,12 @@ class DenseBlock:
         r, c = C.c_int64(0), C.c_int64(0)
         self.ctx.check(self.ctx.lib.sla_dense_dims(self.h, C.byref(r), C.byref(c)))
         return r.value, c.value
+
+    def column(self, j):
+        """Column j as a new SpVector (extractCol of the reference's Q)."""
+        v = C.c_void_p()
+        self.ctx.check(self.ctx.lib.sla_dense_column(self.ctx.h, self.h, j, C.byref(v)))
+        return SpVector(self.ctx, v)
 
     def toHost(self):
         r, c = self.dim
@@ -493,6 +502,21 @@ class SpMatrix:
         cc = out if out is not None else DenseMatrix.zeros(self.nrows, b.dim[1], b.dtype, self.ctx)
         self.ctx.check(self.ctx.lib.sla_spmm_dense(self.ctx.h, self.h, b.h, cc.h))
         return cc
+
+    def matMatT(self, bt, out=None):      # aa ##^ b  = aa ## transpose b   (Class.hs:199-200); bt holds b itself, k x n row-major
+        cc = out if out is not None else DenseMatrix.zeros(self.nrows, bt.dim[0], bt.dtype, self.ctx)
+        self.ctx.check(self.ctx.lib.sla_spmm_dense_abt(self.ctx.h, self.h, bt.h, cc.h))
+        return cc
+
+    def tMatMat(self, b, out=None):       # aa #^# b  = transpose aa ## b   (Class.hs:201-203)
+        cc = out if out is not None else DenseMatrix.zeros(self.ncols, b.dim[1], b.dtype, self.ctx)
+        self.ctx.check(self.ctx.lib.sla_spmm_dense_atb(self.ctx.h, self.h, b.h, cc.h))
+        return cc
+
+    def normFrobenius(self):              # sqrt (trace (m ##^ m))   SpMatrix.hs:751-752
+        out = C.c_double(0)
+        self.ctx.check(self.ctx.lib.sla_csr_norm_frobenius(self.ctx.h, self.h, C.byref(out)))
+        return out.value
 
     def __matmul__(self, x):
         return self.matMat(x) if isinstance(x, DenseMatrix) else self.matVec(x)

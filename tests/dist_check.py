@@ -25,6 +25,7 @@ def main():
     ctx = sd.init_context(local)
     seed = 0x5EED0006
     fails = []
+    modes = {}
 
     def check(name, cond):
         if not cond:
@@ -43,6 +44,7 @@ def main():
         else:
             os.environ.pop("SLA_SPMV_PANELS", None)
         A = sd.generate_distributed(ctx, gk, n, k, seed, band)
+        modes[name] = getattr(A, "dist_p2p_mode", 0)
         starts = A.row_starts
         r0, r1 = starts[rank], starts[rank + 1]
         x = sd.generate_vector_slice(ctx, n, seed + 1, starts, rank)
@@ -56,6 +58,7 @@ def main():
             rp, cj, vv = Ao.toCSR()
             xa = np.abs(xo.toDenseListSV())
             mag = np.add.reduceat(np.abs(vv) * xa[cj], rp[:-1]) if len(vv) else np.zeros(n)
+            mag[np.diff(rp) == 0] = 0.0             # reduceat returns the next element for an empty row
             bound = (np.diff(rp) + 2) * 2.0 ** -53 * mag
             check(f"{name}: row-partitioned (#>) within the fp64 bound (arrival order)", bool(np.all(np.abs(y - yo[r0:r1]) <= bound[r0:r1])))
         else:
@@ -86,16 +89,15 @@ def main():
             xg_, itg, resg = sla.gmres(A, b, sla.SpVector.zeroSV(r1 - r0), restart=20, tol_abs=1e-10, tol_rel=1e-12, info=True)
             check(f"{name}: gmres residual {resg}", resg <= 1e-8)
         # (##) with a dense right operand, row-partitioned: every rank holds the matching row slice of B; fp64 is bit-exact
-        # (written after the round-1 GPU budget was spent: runs only with SLA_DIST_CHECK_EXPERIMENTAL=1 until it has been
-        # seen green on hardware, so that an unvalidated path cannot fail the suite)
-        if name in ("uniform", "laplace", "ragged") and os.environ.get("SLA_DIST_CHECK_EXPERIMENTAL") == "1":
+        # (first seen green on hardware in round 2: profiles/r02_dist_check_*.log)
+        if name in ("uniform", "laplace", "ragged"):
             kk = 5
             Bh = np.random.default_rng(seed + 7).standard_normal((n, kk))
             Cl = A.matMat(sla.DenseMatrix.fromHost(Bh[r0:r1])).toHost()
             Co = Ao.matMat(ora.SpMatrix.fromListDenseSM(n, Bh.T.reshape(-1))).toDense()
             check(f"{name}: row-partitioned (##) bit-exact", Cl.tobytes() == np.ascontiguousarray(Co[r0:r1]).tobytes())
-        # transposeSM / (<#) / CGNE on the row-partitioned matrix (same gate: not yet seen green on hardware)
-        if name in ("uniform", "banded", "ragged") and os.environ.get("SLA_DIST_CHECK_EXPERIMENTAL") == "1":
+        # transposeSM / (<#) / CGNE on the row-partitioned matrix
+        if name in ("uniform", "banded", "ragged"):
             T = sd.transpose_distributed(ctx, A)
             rpT, ciT, vaT = T.toCSR()
             rpo, cio, vao = Ao.transpose().toCSR()
@@ -105,7 +107,16 @@ def main():
             check(f"{name}: distributed transpose val", np.asarray(vaT).tobytes() == np.ascontiguousarray(vao[lo_:hi_], dtype=np.float64).tobytes())
             z = A.vecMat(x, out=sla.SpVector.zeroSV(r1 - r0)).toDenseListSV()
             zo = Ao.vecMat(xo).toDenseListSV()
-            check(f"{name}: row-partitioned (<#) bit-exact", z.tobytes() == zo[r0:r1].tobytes())
+            if getattr(T, "dist_p2p_mode", 0) == 2:
+                # the transpose has its own arrival-order exchange: rotated fold, bounded like (#>) above
+                rpt, cjt, vvt = Ao.transpose().toCSR()
+                xa = np.abs(xo.toDenseListSV())
+                magt = np.add.reduceat(np.abs(vvt) * xa[cjt], rpt[:-1]) if len(vvt) else np.zeros(n)
+                magt[np.diff(rpt) == 0] = 0.0
+                boundt = (np.diff(rpt) + 2) * 2.0 ** -53 * magt
+                check(f"{name}: row-partitioned (<#) within the fp64 bound (arrival order)", bool(np.all(np.abs(z - zo[r0:r1]) <= boundt[r0:r1])))
+            else:
+                check(f"{name}: row-partitioned (<#) bit-exact", z.tobytes() == zo[r0:r1].tobytes())
             st = sla.cgneInit(A, b, sla.SpVector.zeroSV(r1 - r0))
             sto = ora.cgneInit(Ao, bo, ora.SpVector.mkSpVR(n, np.zeros(n)))
             for it in range(3):
@@ -126,7 +137,8 @@ def main():
     flat = [f for fl in all_fails for f in fl]
     if rank == 0:
         print("DIST_CHECK", "OK" if not flat else "FAIL", f"world={world}",
-              "collectives=" + ("p2p" if getattr(ctx, "p2p", False) else "nccl"), "x_exchange_mode=" + os.environ.get("SLA_P2P_X", "0"), flush=True)
+              "collectives=" + ("p2p" if getattr(ctx, "p2p", False) else "nccl"), "x_exchange_mode=" + os.environ.get("SLA_P2P_X", "auto"),
+              "modes_seen=" + ",".join(f"{k}:{v}" for k, v in sorted(modes.items())), flush=True)
         for f in flat:
             print("  ", f, flush=True)
     dist.barrier()

@@ -20,6 +20,12 @@ class _Vec:
     def copy(self):
         return _Vec(self.dim)
 
+    def norm2(self):
+        return 1.0
+
+    def __sub__(self, other):
+        return _Vec(self.dim)
+
 
 class _Mat:
     nnz = 320_000_000
@@ -71,6 +77,9 @@ class _Ctx:
     def pinned(self, n):
         return np.zeros(n)
 
+    def set_option(self, name, value):
+        pass
+
 
 def _fake_backend():
     sla = types.ModuleType("sparse_linear_algebra_b200")
@@ -82,7 +91,8 @@ def _fake_backend():
     sla.SpMatrix = types.SimpleNamespace(generate=lambda kind, n, k, seed, band=0: _Mat(n))
     sla.SpVector = types.SimpleNamespace(zeroSV=lambda n: _Vec(n))
     sla.DenseMatrix = types.SimpleNamespace(generate=lambda *a: object(), zeros=lambda *a: object())
-    sla.bicgsInit = lambda A, b, x0: types.SimpleNamespace(r=_Vec(b.dim))
+    sla.bicgsInit = lambda A, b, x0: types.SimpleNamespace(r=_Vec(b.dim), x=_Vec(b.dim))
+    sla.gmres = lambda A, b, x0, **kw: (x0, 300, 1e-9) if kw.get("info") else x0
     sla.bicgstabStep = lambda A, r, st: st
     sla.arnoldi = lambda A, b, kn: (object(), None, False)
     sla.triLowerSolve = lambda M, rhs, out=None: out
@@ -101,6 +111,8 @@ def test_bench_line_contract(monkeypatch):
     import bench
 
     monkeypatch.setattr(bench, "cpu_baseline", lambda threads, **k: (20.0, 0.03, "sample", 0.6))
+    monkeypatch.setattr(bench, "parity_cfg2", lambda *a, **k: {"rows": 300, "bit_exact_rows": 300, "max_err_over_bound": 0.0, "ok": True})
+    monkeypatch.setattr(bench, "load_traffic", lambda: (4.2e9, 2.1e9, 2, "fake capture"))
     monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
     monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 1})
     args = types.SimpleNamespace(gpus=1, steps=5, warmup=3, impl="b200", quick=False, no_cpu=False, no_sptrsv=False,
@@ -112,7 +124,7 @@ def test_bench_line_contract(monkeypatch):
     assert len(lines) == 1
     d = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-                "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "cpu_baseline"):
+                "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "cpu_baseline", "parity_check", "step_ms"):
         assert key in d, key
     assert d["metric"] == "csr_spmv_fp64_gbs" and d["unit"] == "GB/s" and d["n_gpus"] == 1 and d["vs_baseline"] is None
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
@@ -121,7 +133,8 @@ def test_bench_line_contract(monkeypatch):
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] == 80_000_000
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
     assert d["gpu_launches"] > 0 and "workload" in d["config"] and "model" not in d["config"]
-    for key in ("spmv_banded_gbs", "bicgstab_cfg3_iters_per_s", "arnoldi_cfg4_steps_per_s", "spmm_cfg5_k16_ms", "sptrsv_cfg3_lower_ms"):
+    assert d["parity_check"]["ok"] is True and d["extra"]["bicgstab_cfg3_parity"]["ok"] is True
+    for key in ("spmv_banded_gbs", "bicgstab_cfg3_iters_per_s", "arnoldi_cfg4_steps_per_s", "gmres_cfg4_cycles_per_s", "spmm_cfg5_k16_ms", "sptrsv_cfg3_lower_ms"):
         assert key in d["extra"], key
 
 
@@ -130,7 +143,7 @@ def test_reference_arm_contract(monkeypatch, ora):
 
     monkeypatch.delenv("RANK", raising=False)
     args = types.SimpleNamespace(gpus=1, steps=1, warmup=3, impl="reference")
-    # a small sample keeps the CPU test short; the shipped default is 2 M rows
+    # a small sample keeps the CPU test short; the shipped default is config 2 itself (10 M rows) when the host memory allows
     real_synth = ora.SpMatrix.synth
     monkeypatch.setattr(ora.SpMatrix, "synth", staticmethod(lambda kind, n, k, seed, band=0: real_synth(kind, 20000, k, seed, band)))
     real_vsynth = ora.SpVector.synth

@@ -211,3 +211,55 @@ def test_plan_exchange_properties():
                     assert got[lo:hi + 1].all(), "a referenced column is neither local nor received"
 
     check()
+
+
+# ---- LL halo plan (p2p mode 3): compact indices agree between sender and receiver --------------------------------------
+from sparse_linear_algebra_b200 import dist as sd  # noqa: E402
+
+def _banded_needs(starts, h, n):
+    return [(max(0, starts[p] - h), min(n - 1, starts[p + 1] - 1 + h)) for p in range(len(starts) - 1)]
+
+
+@pytest.mark.parametrize("world,n,h", [(2, 1000, 7), (4, 4096, 64), (8, 96 * 96, 96), (8, 1003, 200), (3, 100, 40)])
+def test_halo_bases_agree_between_sender_and_receiver(world, n, h):
+    starts = sd.row_partition(n, world)
+    needs = _banded_needs(starts, h, n)
+    assert sd.halo_eligible(starts, needs)
+    plans = [sd.plan_exchange(q, starts, needs) for q in range(world)]
+    bases = [sd.halo_bases(q, starts, needs) for q in range(world)]
+    for q in range(world):
+        b, total = bases[q]
+        recv = [(b[i], plans[q][i][3]) for i in range(len(plans[q])) if plans[q][i][0] == 0]
+        # receive segments tile [0, total) without gaps or overlap
+        recv.sort()
+        pos = 0
+        for off, cnt in recv:
+            assert off == pos
+            pos += cnt
+        assert pos == total == sum(c for d, _, _, c in plans[q] if d == 0)
+        # every send lands exactly where the destination expects the matching receive
+        for i, (d, peer, goff, cnt) in enumerate(plans[q]):
+            if d != 1:
+                continue
+            j = next(k for k, (d2, p2, g2, c2) in enumerate(plans[peer]) if d2 == 0 and p2 == q)
+            assert plans[peer][j][2:] == (goff, cnt)
+            assert bases[peer][0][j] == b[i]
+
+
+def test_halo_not_eligible_for_one_sided_or_empty_plans():
+    starts = sd.row_partition(100, 2)
+    # rank 0 needs a piece of rank 1's block, rank 1 needs nothing from rank 0: one-sided -> no LL halo (no implicit barrier)
+    assert not sd.halo_eligible(starts, [(0, 60), (50, 99)])
+    # block diagonal: nothing travels
+    assert not sd.halo_eligible(starts, [(0, 49), (50, 99)])
+
+
+def test_exchange_mode_env(monkeypatch):
+    monkeypatch.delenv("SLA_P2P", raising=False)
+    monkeypatch.delenv("SLA_P2P_X", raising=False)
+    assert sd.p2p_exchange_mode() == -1
+    for v, want in (("auto", -1), ("0", 0), ("2", 2), ("3", 3), ("9", 4), ("x", -1)):
+        monkeypatch.setenv("SLA_P2P_X", v)
+        assert sd.p2p_exchange_mode() == want
+    monkeypatch.setenv("SLA_P2P", "0")
+    assert sd.p2p_exchange_mode() == 0

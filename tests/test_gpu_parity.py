@@ -645,3 +645,129 @@ def test_full_size_bicgstab_cfg3(sla, o):
     true_res = ((A @ st.x) - b).norm2()
     assert abs(true_res - st.r.norm2()) <= 1e-8 * r0
     assert true_res < 0.5 * r0
+
+
+# =============================================================== round 2: pure Krylov records, fixed-work GMRES, Arnoldi bookkeeping on the device
+
+def test_krylov_clone_gives_pure_steps(sla, o):
+    """README.md:208 — `iterate (bicgstabStep amat r0hat) initState !! k` keeps initState alive: a pure step (clone, then
+    advance the clone) leaves its argument untouched and follows the same trajectory as the in-place step."""
+    n, k, seed = 3000, 12, 0x5EED0011
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+    b = A @ sla.SpVector.generate(n, seed + 1)
+    for init, step in ((sla.bicgsInit, sla.bicgstabStep), (sla.cgsInit, sla.cgsStep)):
+        st0 = init(A, b, sla.SpVector.zeroSV(n))
+        rhat = st0.r.copy()
+        x0, r0, p0 = st0.x.toDenseListSV(), st0.r.toDenseListSV(), st0.p.toDenseListSV()
+        seq = [st0]
+        for _ in range(4):
+            seq.append(step(A, rhat, seq[-1], pure=True))
+        # the argument of every pure step is unchanged
+        assert st0.x.toDenseListSV().tobytes() == x0.tobytes() and st0.r.toDenseListSV().tobytes() == r0.tobytes()
+        assert st0.p.toDenseListSV().tobytes() == p0.tobytes()
+        # same bits as the in-place recurrence
+        st = init(A, b, sla.SpVector.zeroSV(n))
+        for j in range(1, 5):
+            step(A, rhat, st)
+            assert st.x.toDenseListSV().tobytes() == seq[j].x.toDenseListSV().tobytes(), j
+            assert st.r.toDenseListSV().tobytes() == seq[j].r.toDenseListSV().tobytes(), j
+    stc = sla.cgneInit(A, b, sla.SpVector.zeroSV(n))
+    st1 = sla.cgneStep(A, stc, pure=True)
+    assert np.array_equal(stc.x.toDenseListSV(), np.zeros(n)) and np.abs(st1.x.toDenseListSV()).max() > 0
+
+
+def test_rho_cache_survives_vector_reuse(sla):
+    """the cached rho = r <.> r0hat must not be reused for a NEW shadow residual that the allocator happens to
+    place where the freed one lived (stamps are unique per context now)."""
+    n, k, seed = 2048, 8, 0x5EED0012
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+    b = A @ sla.SpVector.generate(n, seed + 1)
+    st = sla.bicgsInit(A, b, sla.SpVector.zeroSV(n))
+    ref = sla.bicgsInit(A, b, sla.SpVector.zeroSV(n))
+    rhat = st.r.copy()
+    sla.bicgstabStep(A, rhat, st)
+    sla.bicgstabStep(A, ref.r.copy(), ref)
+    del rhat                                            # freed; the next vector of this size is likely to reuse the address
+    other = 2.0 * ref.r.copy()                          # a different shadow residual
+    sla.bicgstabStep(A, other, st)
+    sla.bicgstabStep(A, 2.0 * ref.r.copy(), ref)        # reference: fresh vector, no cache hit possible by pointer
+    assert st.x.toDenseListSV().tobytes() == ref.x.toDenseListSV().tobytes()
+
+
+def test_gmres_fixed_work_runs_every_cycle(sla):
+    """BASELINE config 4 is "GMRES(30), 10 restarts": with the stopping test off every cycle runs to its end."""
+    n, k, seed = 4000, 16, 0x5EED0004
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+    xt = sla.SpVector.generate(n, seed + 2)
+    b = A @ xt
+    x, it, res = sla.gmres(A, b, sla.SpVector.zeroSV(n), restart=10, nits=40, fixed_work=True, info=True)
+    assert it == 40
+    assert np.isfinite(res) and res <= 1e-6 * b.norm2()
+    np.testing.assert_allclose(x.toDenseListSV(), xt.toDenseListSV(), atol=1e-6)
+    # with the stopping test the same problem stops early, mid-cycle, with the same answer
+    x2, it2, res2 = sla.gmres(A, b, sla.SpVector.zeroSV(n), restart=10, nits=40, tol_abs=1e-8, tol_rel=1e-12, info=True)
+    assert it2 < 40 and res2 <= 1e-8
+    np.testing.assert_allclose(x2.toDenseListSV(), xt.toDenseListSV(), atol=1e-6)
+
+
+def test_arnoldi_long_basis_and_breakdown(sla, o):
+    """More than 32 basis columns (two launches of the dot kernel per step) against the oracle, and a breakdown found after
+    the whole run was queued: the columns computed past it are discarded, H is the reference's (nmax+1) x nmax block."""
+    n, k, seed, kn = 1500, 10, 0x5EED0021, 40
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+    Ao = o.SpMatrix.synth(o.GEN_UNIFORM, n, k, seed)
+    Qd, H, brk = sla.arnoldi(A, sla.SpVector.generate(n, seed + 1), kn)
+    assert not brk and H.shape == (kn + 1, kn)
+    Q = Qd.toHost()
+    Ad = Ao.toDense()
+    assert np.linalg.norm(Ad @ Q[:, :-1] - Q @ H) / np.linalg.norm(Ad) <= 1e-12 * np.sqrt(n)
+    Qo, Ho = o.arnoldi(Ao, o.SpVector.synth(seed + 1, n), kn)
+    np.testing.assert_allclose(H[:, :8], Ho[:, :8], atol=1e-9 * np.abs(Ho).max())
+    # invariant subspace after 2 steps: diag(1, 2, 3, ...) applied to e0 + e1
+    D = sla.SpMatrix.mkDiagonal(50, np.arange(1.0, 51.0))
+    Do = o.SpMatrix.fromListSM((50, 50), [(i, i, float(i + 1)) for i in range(50)])
+    v = np.zeros(50); v[0] = v[1] = 1.0
+    Qb, Hb, brkb = sla.arnoldi(D, sla.SpVector.mkSpVR(50, v), 10)
+    Qob, Hob = o.arnoldi(Do, o.SpVector.mkSpVR(50, v), 10)
+    assert brkb and Hb.shape == Hob.shape and Qb.toHost().shape == Qob.shape
+    good = Hb.shape[1] - 1
+    np.testing.assert_allclose(Hb[:, :good], Hob[:, :good], atol=1e-12)
+
+
+def test_spmv_bulk_staging_bit_exact(sla, o, monkeypatch):
+    """The bulk-copy staged variant of the tile kernel (option "spmv_bulk": the (col, val) tile arrives through cp.async.bulk
+    instead of LDG) computes the same bits: plain, column panels, long rows, fused Krylov epilogues."""
+    ctx = sla.default_context()
+    rng = np.random.default_rng(77)
+    cases = []
+    for (m, n, k) in ((1, 1, 1), (300, 200, 2500), (5000, 4000, 60000)):
+        i, j, v = _rand_coo(rng, m, n, k, long_rows=((0, min(n, 700)),) if m > 1 else ())
+        cases.append(((m, n), i, j, v))
+    try:
+        for dims, i, j, v in cases:
+            x = rng.standard_normal(dims[1])
+            for panels in ("1", "3"):
+                monkeypatch.setenv("SLA_SPMV_PANELS", panels)
+                A = sla.SpMatrix.fromCOO(dims, i, j, v)
+                xs = sla.SpVector.mkSpVR(dims[1], x)
+                ctx.set_option("spmv_bulk", 0)
+                y0 = (A @ xs).toDenseListSV()
+                ctx.set_option("spmv_bulk", 1)
+                y1 = (A @ xs).toDenseListSV()
+                assert y0.tobytes() == y1.tobytes(), (dims, panels)
+        monkeypatch.delenv("SLA_SPMV_PANELS", raising=False)
+        # a Krylov trajectory (fused dot epilogues ride on the same kernel)
+        n, k, seed = 4096, 16, 0x5EED0031
+        A = sla.SpMatrix.generate(sla.GEN_UNIFORM, n, k, seed)
+        b = A @ sla.SpVector.generate(n, seed + 1)
+        xs = []
+        for bulk in (0, 1):
+            ctx.set_option("spmv_bulk", bulk)
+            st = sla.bicgsInit(A, b, sla.SpVector.zeroSV(n))
+            rhat = st.r.copy()
+            for _ in range(5):
+                sla.bicgstabStep(A, rhat, st)
+            xs.append(st.x.toDenseListSV())
+        assert xs[0].tobytes() == xs[1].tobytes()
+    finally:
+        ctx.set_option("spmv_bulk", int(__import__("os").environ.get("SLA_SPMV_BULK", "0")))
