@@ -103,11 +103,12 @@ sla_status sla_p2p_attach(sla_ctx*, const void* handles /* world x 64 bytes */);
 sla_status sla_p2p_enable(sla_ctx*, int on);
 int        sla_p2p_enabled(const sla_ctx*);
 /* LL halo exchange (mode 3): base[s] belongs to segment s of the plan given to sla_csr_set_dist — the compact offset of the
- * segment in this rank's halo buffer (receive) or in the destination's (send).  Call before sla_csr_p2p_export. */
-sla_status sla_csr_set_halo(sla_ctx*, sla_csr*, int nseg, const int64_t* base);
+ * segment in this rank's halo buffer (receive) or in the destination's (send); capacity = entries of the LARGEST halo of the
+ * job (the same value on every rank: all halo buffers have one size).  Call before sla_csr_p2p_export. */
+sla_status sla_csr_set_halo(sla_ctx*, sla_csr*, int nseg, const int64_t* base, int64_t capacity);
 sla_status sla_csr_p2p_export(sla_ctx*, sla_csr*, void* handle64);
 sla_status sla_csr_p2p_attach(sla_ctx*, sla_csr*, const void* handles /* world x 64 bytes */);
-sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on /* 0 off, 1 push kernel, 2 copy engines + arrival-order panels, 3 LL halo */);
+sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on /* 0 off, 1 push kernel, 2 copy engines + arrival-order panels, 3 LL halo, 4 copy-engine all-gather */);
 int        sla_csr_p2p_mode(const sla_csr*);      /* the mode in force (2 falls back to 1 when the plan is not dense / equal-block) */
 /* transposeSM of a row-partitioned square matrix (all-to-all of entries; starts = world + 1 global row offsets, the same on
  * every rank): *out is this rank's row block of the transpose; give it an exchange plan like any block, then hand it to A

@@ -57,7 +57,7 @@ SIGNATURES = {
     "sla_csr_generate_rows": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_uint64, _i64, _i64, _i64, _pp]),
     "sla_csr_col_range": (C.c_int, [_p, _p, _pi64, _pi64]),
     "sla_csr_set_dist": (C.c_int, [_p, _p, _i64, C.c_int, _pint, _pint, _pi64, _pi64, C.c_int]),
-    "sla_csr_set_halo": (C.c_int, [_p, _p, C.c_int, _pi64]),
+    "sla_csr_set_halo": (C.c_int, [_p, _p, C.c_int, _pi64, _i64]),
     "sla_csr_transpose_dist": (C.c_int, [_p, _p, _pi64, _pp]),
     "sla_csr_attach_transpose": (C.c_int, [_p, _p, _p]),
     "sla_p2p_export": (C.c_int, [_p, _p]),

@@ -285,7 +285,7 @@ void sla_p2p_free(sla_ctx* c) {
 // LL halo plan: base[s] belongs to segment s of the plan given to sla_csr_set_dist — for a receive segment the compact
 // offset of its first entry in this rank's halo buffer, for a send segment the offset in the destination's buffer (the
 // host derives both from the global table of column ranges, dist.py).  Call before sla_csr_p2p_export.
-extern "C" sla_status sla_csr_set_halo(sla_ctx* c, sla_csr* A, int nseg, const int64_t* base) {
+extern "C" sla_status sla_csr_set_halo(sla_ctx* c, sla_csr* A, int nseg, const int64_t* base, int64_t capacity) {
   if (!c || !A || !A->dist || nseg < 0 || (nseg > 0 && !base)) return SLA_ERR_INVALID;
   sla_dist_info* d = A->dist;
   if (nseg != d->nseg) return sla_fail(c, SLA_ERR_INVALID, "set_halo: one base per exchange segment expected");
@@ -297,6 +297,8 @@ extern "C" sla_status sla_csr_set_halo(sla_ctx* c, sla_csr* A, int nseg, const i
     if (d->seg[s].dir == 0) { ++nrecv; if (base[s] + d->seg[s].count > total) total = base[s] + d->seg[s].count; }
   }
   (void)nrecv;
+  if (capacity < total) return sla_fail(c, SLA_ERR_INVALID, "set_halo: capacity is smaller than this rank's halo");
+  total = capacity;                             // one buffer size for the whole job: senders address peers' buffers with their own stride
   if (total >= (int64_t)1 << 31) return sla_fail(c, SLA_ERR_INVALID, "set_halo: halo too large");
   delete[] d->seg_base;
   d->seg_base = new (std::nothrow) int64_t[nseg > 0 ? nseg : 1];

@@ -102,7 +102,10 @@ def p2p_exchange_mode():
         3  LL halo (symmetric halo plans): ONE kernel stores 16-byte tagged entries straight into the neighbours' halo
            buffers and unpacks the entries arriving from them — no fence, no flag round trip, no rendezvous
         4  copy-engine all-gather waited for as a whole (what 2 degrades to)
-    Automatic = 2 for dense equal-block plans, 3 for eligible halo plans, NCCL otherwise.  Must agree on every rank."""
+    Automatic (measured on B200, profiles/r02_*): 2 for dense equal-block plans on TWO ranks (cfg 2: 0.824 vs 0.933 ms, the
+    exchange fully hidden), NCCL otherwise — at 8 ranks the seven copy-engine transfers per rank took 0.43 ms against 0.16 ms
+    for ncclAllGather (cfg 2: 0.654 vs 0.388 ms), and the LL halo kernel only equals NCCL's grouped send/recv (11 us exposed
+    per (#>) on the 4096^2 Laplacian either way), so 3 and 4 stay opt-in.  Must agree on every rank."""
     if not p2p_wanted():
         return 0
     v = os.environ.get("SLA_P2P_X", "auto")
@@ -235,7 +238,7 @@ def distribute(ctx, A, starts):
     mode = p2p_exchange_mode()
     halo_ok = not dense and halo_eligible(starts, needs)
     if mode == -1:
-        mode = 2 if allgather else (3 if halo_ok else 0)
+        mode = 2 if allgather and world == 2 else 0
     elif mode == 3 and not halo_ok:
         mode = 0
     elif mode in (2, 4) and not allgather:
@@ -244,8 +247,11 @@ def distribute(ctx, A, starts):
         lib = ctx.lib
         if mode == 3:
             bases, _ = halo_bases(rank, starts, needs)
+            # every rank's halo buffer gets the SAME capacity (the largest halo of the job): a sender addresses the second
+            # buffer of a peer's window with its own stride
+            cap = max(halo_bases(q, starts, needs)[1] for q in range(world))
             arr = (C.c_int64 * max(len(bases), 1))(*bases)
-            ctx.check(lib.sla_csr_set_halo(ctx.h, A.h, len(bases), arr))
+            ctx.check(lib.sla_csr_set_halo(ctx.h, A.h, len(bases), arr, cap))
         A.dist_p2p = _p2p_handshake(lambda buf: lib.sla_csr_p2p_export(ctx.h, A.h, buf),
                                     lambda blob: lib.sla_csr_p2p_attach(ctx.h, A.h, blob),
                                     lambda on: ctx.check(lib.sla_csr_p2p_enable(ctx.h, A.h, mode if on else 0)))
