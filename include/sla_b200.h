@@ -230,6 +230,11 @@ sla_status sla_csr_norm_frobenius(sla_ctx*, const sla_csr* A, double* out);
 sla_status sla_csr_diag_partitions(sla_ctx*, const sla_csr* A, sla_csr** E, sla_csr** D, sla_csr** F);
 sla_status sla_jacobi_pre(sla_ctx*, const sla_csr* A, sla_csr** M);
 sla_status sla_mssor_pre(sla_ctx*, const sla_csr* A, double omega, sla_csr** L, sla_csr** R);
+/* ilu0Pre aa = (l, u) with holes (Sparse.hs:696-706): the reference runs the COMPLETE Doolittle `lu` (Sparse.hs:489-538) and then
+ * drops the entries of L and U where aa stores nothing — not the incomplete recurrence of the literature.  The same recurrences,
+ * in the same order, on a dense work area: bit-identical to the reference's evaluation, n <= 4096 (its algorithm is O(n^3)).
+ * A nearZero pivot returns SLA_ERR_NEEDS_PIVOTING ("solveForLij : U(j,j) is close to 0 ..."). */
+sla_status sla_ilu0_pre(sla_ctx*, const sla_csr* A, sla_csr** L, sla_csr** U);
 sla_status sla_tri_lower_solve(sla_ctx*, const sla_csr* L, const sla_vec* b, sla_vec* w);
 sla_status sla_tri_upper_solve(sla_ctx*, const sla_csr* U, const sla_vec* w, sla_vec* x);
 sla_status sla_tri_analysis(sla_ctx*, const sla_csr* A, int upper, int* nlevels, int64_t* nnz_tri);

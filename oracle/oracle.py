@@ -100,6 +100,8 @@ def lib():
         "ora_sm_sub": (_p, [_p, _p]),
         "ora_jacobi_pre": (_p, [_p]),
         "ora_mssor_pre": (C.c_int, [_p, _f64, C.POINTER(_p), C.POINTER(_p)]),
+        "ora_lu": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(C.c_int64)]),
+        "ora_ilu0_pre": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(C.c_int64)]),
         "ora_tri_lower_solve": (_p, [_p, _p, _pint, _pi64]),
         "ora_tri_upper_solve": (_p, [_p, _p, _pint, _pi64]),
         "ora_krylov_free": (None, [C.POINTER(_Krylov)]),
@@ -437,6 +439,24 @@ def mSsorPre(aa, omega):       # Sparse.hs:713-721
     if err:
         raise OracleError(err, "matMat : incompatible matrix sizes")
     return SpMatrix(l.value), SpMatrix(r.value)
+
+
+def _lu(fn, what, aa):
+    l, u, bad = _p(), _p(), C.c_int64(-1)
+    err = fn(aa._h, C.byref(l), C.byref(u), C.byref(bad))
+    if err == 4:
+        raise NeedsPivoting(what, bad.value)
+    if err:
+        raise OracleError(err, what)
+    return SpMatrix(l.value), SpMatrix(u.value)
+
+
+def lu(aa):                    # Sparse.hs:489-538
+    return _lu(lib().ora_lu, "solveForLij", aa)
+
+
+def ilu0Pre(aa):               # Sparse.hs:696-706
+    return _lu(lib().ora_ilu0_pre, "solveForLij", aa)
 
 
 def _tri(fn, what, mm, v):

@@ -534,6 +534,102 @@ int ora_mssor_pre(const ora_sm* aa, double omega, ora_sm** l_out, ora_sm** r_out
   return ORA_OK;
 }
 
+/* m @@! (i, j): lookup with default 0 (no bounds check)   SpMatrix.hs:280-287 */
+static double sm_at(const ora_sm* a, int64_t i, int64_t j) {
+  int found; int64_t p = sm_find_row(a, i, &found);
+  if (!found) return 0.0;
+  int f2; int64_t q = sv_find(a->row[p], j, &f2);
+  return f2 ? a->row[p]->val[q] : 0.0;
+}
+
+static int sm_has(const ora_sm* a, int64_t i, int64_t j) {
+  int found; int64_t p = sm_find_row(a, i, &found);
+  if (!found) return 0;
+  int f2; sv_find(a->row[p], j, &f2);
+  return f2;
+}
+
+/* contractSub a b i j n = foldlWithKey' (\acc k x -> if k > n then acc else acc + x * b @@! (k, j)) 0 (row i of a)
+ * — the STORED entries of row i of a, ascending k, strict left fold from 0   SpMatrix.hs:857-864 */
+static double contract_sub(const ora_sm* a, const ora_sm* b, int64_t i, int64_t j, int64_t n) {
+  int found; int64_t p = sm_find_row(a, i, &found);
+  double acc = 0.0;
+  if (!found) return acc;
+  const ora_sv* row = a->row[p];
+  for (int64_t q = 0; q < row->nnz; ++q) {
+    const int64_t k = row->idx[q];
+    if (k > n) continue;
+    acc = acc + row->val[q] * sm_at(b, k, j);
+  }
+  return acc;
+}
+
+/* lu aa = (L, U), Doolittle (unit diagonal of L)   Sparse.hs:489-538.
+ *   luInit : l0 = insertCol (eye n) (extractSubCol aa 0 (1, n-1) ./ u00) 0 ; u0 = insertRow (zeroSM n n) (extractRow aa 0) 0
+ *            (column 0 of L is a_i0 * recip u00 — `./` multiplies by the reciprocal, Class.hs:94-95; stored entries only)
+ *   step i = 1 .. n-1: U row i : u_ij = a_ij - contractSub L U i j (i-1), j = i .. n-1, kept when isNz (onRangeSparse)
+ *                      L col i : l_ki = (a_ki - contractSub L U k i (k-1)) / u_ii, k = i+1 .. n-1, kept when isNz;
+ *                                a nearZero u_ii throws NeedsPivoting as soon as the range is not empty
+ * *bad = the pivot index on ORA_ERR_NEEDS_PIVOTING.  O(n^3) element at a time, like the reference: small n only. */
+int ora_lu(const ora_sm* aa, ora_sm** l_out, ora_sm** u_out, int64_t* bad) {
+  const int64_t n = aa->nrows;
+  *l_out = *u_out = NULL;
+  if (bad) *bad = -1;
+  if (n < 1 || aa->ncols != n) return ORA_ERR_SIZE_MISMATCH;
+  ora_sm* l = ora_sm_eye(n);
+  ora_sm* u = ora_sm_zero(n, n);
+  {
+    int found; int64_t p = sm_find_row(aa, 0, &found);
+    if (found) for (int64_t q = 0; q < aa->row[p]->nnz; ++q) sm_insert(u, 0, aa->row[p]->idx[q], aa->row[p]->val[q]);   /* extractRow aa 0 */
+  }
+  const double u00 = sm_at(u, 0, 0);
+  if (ora_near_zero(u00)) { ora_sm_free(l); ora_sm_free(u); if (bad) *bad = 0; return ORA_ERR_NEEDS_PIVOTING; }
+  {
+    const double r00 = 1.0 / u00;                                  /* v ./ s = recip s .* v */
+    for (int64_t i = 1; i < n; ++i) if (sm_has(aa, i, 0)) sm_insert(l, i, 0, r00 * sm_at(aa, i, 0));
+  }
+  for (int64_t ix = 1; ix < n; ++ix) {
+    /* uUpd */
+    for (int64_t j = ix; j < n; ++j) {
+      const double v = sm_at(aa, ix, j) - contract_sub(l, u, ix, j, ix - 1);
+      if (!ora_near_zero(v)) sm_insert(u, ix, j, v);
+    }
+    /* lUpd */
+    if (ix + 1 < n) {
+      const double ujj = sm_at(u, ix, ix);
+      if (ora_near_zero(ujj)) { ora_sm_free(l); ora_sm_free(u); if (bad) *bad = ix; return ORA_ERR_NEEDS_PIVOTING; }
+      /* every l_k,ix is computed against L as it was BEFORE this column is inserted (insertCol happens after the list is built) */
+      double* col = (double*)malloc(sizeof(double) * (size_t)n);
+      for (int64_t k = ix + 1; k < n; ++k) col[k] = (sm_at(aa, k, ix) - contract_sub(l, u, k, ix, k - 1)) / ujj;
+      for (int64_t k = ix + 1; k < n; ++k) if (!ora_near_zero(col[k])) sm_insert(l, k, ix, col[k]);
+      free(col);
+    }
+  }
+  *l_out = l; *u_out = u;
+  return ORA_OK;
+}
+
+/* ilu0Pre aa = (sparsifyLU l aa, sparsifyLU u aa) where (l, u) = lu aa and sparsifyLU m m2 keeps the entries of m at the
+ * positions STORED in m2 (ifilterSM (\i j _ -> isJust (lookupSM m2 i j)))   Sparse.hs:696-706.
+ * NB this is the COMPLETE factorisation with the fill-in dropped afterwards, not the classical ILU(0) recurrence. */
+static ora_sm* sm_mask_by(const ora_sm* m, const ora_sm* pat) {
+  ora_sm* out = ora_sm_zero(m->nrows, m->ncols);
+  for (int64_t p = 0; p < m->nstored; ++p)
+    for (int64_t q = 0; q < m->row[p]->nnz; ++q)
+      if (sm_has(pat, m->rkey[p], m->row[p]->idx[q])) sm_insert(out, m->rkey[p], m->row[p]->idx[q], m->row[p]->val[q]);
+  return out;
+}
+
+int ora_ilu0_pre(const ora_sm* aa, ora_sm** l_out, ora_sm** u_out, int64_t* bad) {
+  ora_sm *l = NULL, *u = NULL;
+  const int err = ora_lu(aa, &l, &u, bad);
+  if (err != ORA_OK) return err;
+  *l_out = sm_mask_by(l, aa);
+  *u_out = sm_mask_by(u, aa);
+  ora_sm_free(l); ora_sm_free(u);
+  return ORA_OK;
+}
+
 /* m @@ (i, j): bounds-checked lookup with default 0; out of bounds is `error "@@ : incompatible indices"`.
  * SpMatrix.hs:108-109, 280-287 */
 static int sm_lookup_checked(const ora_sm* a, int64_t i, int64_t j, double* out) {

@@ -90,6 +90,10 @@ ora_sm* ora_sm_add(const ora_sm* a, const ora_sm* b);                     /* (^+
 ora_sm* ora_sm_sub(const ora_sm* a, const ora_sm* b);                     /* (^-^)     Class.hs:68-69 */
 ora_sm* ora_jacobi_pre(const ora_sm* a);                                  /* jacobiPre         Sparse.hs:686-687 */
 int     ora_mssor_pre(const ora_sm* aa, double omega, ora_sm** l, ora_sm** r); /* mSsorPre     Sparse.hs:713-721 */
+/* lu (Doolittle, Sparse.hs:489-538) and ilu0Pre = lu followed by a mask on aa's stored positions (Sparse.hs:696-706);
+ * ORA_ERR_NEEDS_PIVOTING with *bad = the pivot whose u_jj is nearZero.  O(n^3): small matrices only. */
+int     ora_lu(const ora_sm* aa, ora_sm** l, ora_sm** u, int64_t* bad);
+int     ora_ilu0_pre(const ora_sm* aa, ora_sm** l, ora_sm** u, int64_t* bad);
 /* *err: ORA_ERR_NEEDS_PIVOTING (with *bad_row = the row whose diagonal is nearZero) or ORA_ERR_OOB_INDEX (the
  * `@@` lookup past the matrix that a system of dimension 1 runs into). */
 ora_sv* ora_tri_lower_solve(const ora_sm* ll, const ora_sv* b, int* err, int64_t* bad_row);  /* triLowerSolve Sparse.hs:750-777 */

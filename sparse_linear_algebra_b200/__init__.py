@@ -13,5 +13,5 @@ from .sparse import (  # noqa: E402
     BCG_, BF16, BICGSTAB_, CGNE_, CGS_, F64, GMRES_, GEN_BANDED, GEN_BLOCK16, GEN_LAPLACE2D, GEN_UNIFORM, Context, DenseBlock, DenseMatrix, IterE,
     KrylovState, MatVecSizeMismatchException, NeedsPivoting, OutOfBoundsIndexError, SlaError, SpMatrix, SpVector, arnoldi,
     backslash, bicgsInit, bicgstabStep, cgneInit, cgneStep, cgsInit, cgsStep, default_context, diagPartitions, gmres,
-    jacobiPre, linSolve0, linSolve0Host, mSsorPre, set_default_context, triLowerSolve, triUpperSolve,
+    ilu0Pre, jacobiPre, linSolve0, linSolve0Host, mSsorPre, set_default_context, triLowerSolve, triUpperSolve,
 )

@@ -122,6 +122,7 @@ SIGNATURES = {
     "sla_csr_diag_partitions": (C.c_int, [_p, _p, _pp, _pp, _pp]),
     "sla_jacobi_pre": (C.c_int, [_p, _p, _pp]),
     "sla_mssor_pre": (C.c_int, [_p, _p, _f64, _pp, _pp]),
+    "sla_ilu0_pre": (C.c_int, [_p, _p, _pp, _pp]),
     "sla_tri_lower_solve": (C.c_int, [_p, _p, _p, _p]),
     "sla_tri_upper_solve": (C.c_int, [_p, _p, _p, _p]),
     "sla_tri_analysis": (C.c_int, [_p, _p, C.c_int, _pint, _pi64]),

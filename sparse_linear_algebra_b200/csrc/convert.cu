@@ -36,8 +36,12 @@ sla_status sla_csr_alloc(sla_ctx* c, int64_t m, int64_t n, int64_t nnz, sla_csr*
     return sla_fail(c, SLA_ERR_ALLOC, "cudaMalloc failed for a CSR matrix");
   }
   // zero the padding (and everything else) so that tile loads past nnz read col 0 / val 0.0
-  SLA_CUDA(c, cudaMemsetAsync(A->col + nnz, 0, sizeof(int32_t) * (size_t)(pn - nnz), c->stream));
-  SLA_CUDA(c, cudaMemsetAsync(A->val + nnz, 0, sizeof(double) * (size_t)(pn - nnz), c->stream));
+  if (cudaMemsetAsync(A->col + nnz, 0, sizeof(int32_t) * (size_t)(pn - nnz), c->stream) != cudaSuccess ||
+      cudaMemsetAsync(A->val + nnz, 0, sizeof(double) * (size_t)(pn - nnz), c->stream) != cudaSuccess) {
+    cudaGetLastError();
+    sla_csr_free(A);
+    return sla_fail(c, SLA_ERR_CUDA, "cudaMemsetAsync failed for a CSR matrix");
+  }
   *out = A;
   return SLA_OK;
 }

@@ -673,6 +673,13 @@ def mSsorPre(aa, omega):
     return SpMatrix(aa.ctx, l), SpMatrix(aa.ctx, r)
 
 
+def ilu0Pre(aa):
+    """ilu0Pre aa = (l, u) with holes: the reference's complete `lu` masked by aa's stored positions (Sparse.hs:696-706)."""
+    l, u = C.c_void_p(), C.c_void_p()
+    aa.ctx.check(aa.ctx.lib.sla_ilu0_pre(aa.ctx.h, aa.h, C.byref(l), C.byref(u)))
+    return SpMatrix(aa.ctx, l), SpMatrix(aa.ctx, u)
+
+
 def triLowerSolve(ll, b, out=None):
     """triLowerSolve ll b: forward substitution (Sparse.hs:750-777); raises NeedsPivoting on a nearZero diagonal."""
     w = out if out is not None else SpVector.zeroSV(b.dim, ll.ctx)

@@ -245,3 +245,44 @@ def test_full_size_laplacian_sweeps(sla):
     x = sla.triUpperSolve(A, b)
     res = ((d @ x) + (f @ x)) - b
     assert res.norm2() <= 1e-12 * b.norm2()
+
+
+# ---- ilu0Pre (Sparse.hs:696-706): the reference's complete lu masked by aa's stored positions, bit-exact -------------------
+
+@pytest.mark.parametrize("n,density,seed", [(1, 1.0, 0), (2, 1.0, 1), (5, 0.6, 2), (17, 0.4, 3), (50, 0.2, 4), (50, 1.0, 5), (300, 0.03, 6)])
+def test_ilu0pre_bit_exact(sla, o, n, density, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n)) * (rng.random((n, n)) < density) + np.diag(rng.uniform(3, 5, n) * n ** 0.5)
+    trip = [(i, j, A[i, j]) for i in range(n) for j in range(n) if A[i, j] != 0.0]
+    lo, uo = o.ilu0Pre(o.SpMatrix.fromListSM((n, n), trip))
+    lg, ug = sla.ilu0Pre(sla.SpMatrix.fromListSM((n, n), trip))
+    assert csr_equal(lg, lo)
+    assert csr_equal(ug, uo)
+
+
+def test_ilu0pre_reference_fixtures_and_errors(sla, o):
+    import math
+
+    for dims, trip in (((2, 2), [(0, 0, 1.0), (1, 0, 3.0), (0, 1, 2.0), (1, 1, 4.0)]),
+                       ((2, 2), [(0, 0, math.pi), (1, 0, math.sqrt(2)), (0, 1, math.e), (1, 1, math.sqrt(5))]), F.tm7_triples()):
+        lo, uo = o.ilu0Pre(o.SpMatrix.fromListSM(dims, trip))
+        lg, ug = sla.ilu0Pre(sla.SpMatrix.fromListSM(dims, trip))
+        assert csr_equal(lg, lo) and csr_equal(ug, uo)
+        # tridiagonal / dense 2 x 2: no fill-in, so the masked factors still multiply back to aa (checkLu, LibSpec.hs:424-434)
+        d = lg.toDense() @ ug.toDense() - sla.SpMatrix.fromListSM(dims, trip).toDense()
+        assert np.abs(d).max() <= 1e-12
+    # explicit zeros stored in aa keep their positions in the mask; a stored 0 in column 0 is a stored 0 in L
+    trip = [(0, 0, 2.0), (1, 0, 0.0), (1, 1, 3.0), (0, 1, 0.0), (2, 2, 1.0), (2, 0, 4.0)]
+    lo, uo = o.ilu0Pre(o.SpMatrix.fromListSM((3, 3), trip))
+    lg, ug = sla.ilu0Pre(sla.SpMatrix.fromListSM((3, 3), trip))
+    assert csr_equal(lg, lo) and csr_equal(ug, uo)
+    # NeedsPivoting: u00 = 0, and a pivot that cancels at step 1 (same pivot index as the oracle)
+    for trip, dims in (([(0, 1, 1.0), (1, 0, 1.0)], (2, 2)),
+                       ([(0, 0, 1.0), (0, 1, 1.0), (1, 0, 1.0), (1, 1, 1.0), (2, 2, 1.0), (2, 1, 1.0)], (3, 3))):
+        with pytest.raises(o.NeedsPivoting) as eo:
+            o.ilu0Pre(o.SpMatrix.fromListSM(dims, trip))
+        with pytest.raises(sla.NeedsPivoting) as eg:
+            sla.ilu0Pre(sla.SpMatrix.fromListSM(dims, trip))
+        assert f"U({eo.value.row},{eo.value.row})" in str(eg.value)
+    with pytest.raises(sla.SlaError):
+        sla.ilu0Pre(sla.SpMatrix.generate(sla.GEN_UNIFORM, 5000, 4, 1))     # beyond the O(n^3) algorithm's range

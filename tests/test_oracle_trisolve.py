@@ -94,3 +94,64 @@ def test_diag_partitions_and_preconditioners(o):
     assert l2.toDense().tolist() == [[0.5, 0, 0], [0.0 + 0.5 * -(4 * 2.0), 0, 0], [0, 0, 0.2]]
     assert r2.toDense().tolist() == [[2, 0, 0], [0, 0, 0], [0, 0, 5]]
     assert o.jacobiPre(bb).nnz == 2
+
+
+# ---- lu / ilu0Pre (Sparse.hs:489-538, 696-706): the reference's own specs (LibSpec.hs:184-194, checkLu :424-434) ------------
+
+def _check_lu(o, aa):
+    """checkLu: nearZero (normFrobenius (sparsifySM ((l ## u) ^-^ a))) && isUpperTriSM u && isLowerTriSM l"""
+    l, u = o.lu(aa)
+    L, U, A = l.toDense(), u.toDense(), aa.toDense()
+    d = L @ U - A
+    d[np.abs(d) <= 1e-12] = 0.0
+    return np.sqrt((d * d).sum()) <= 1e-12 and np.allclose(U, np.triu(U)) and np.allclose(L, np.tril(L)), L, U
+
+
+def test_ref_lu_specs(ora):
+    o = ora
+    import math
+
+    aa0 = o.SpMatrix.fromListDenseSM(*F.AA0)                                             # "lu (2 x 2 dense)"
+    tm0 = o.SpMatrix.fromListSM((2, 2), [(0, 0, math.pi), (1, 0, math.sqrt(2)), (0, 1, math.e), (1, 1, math.sqrt(5))])   # "lu (2 x 2 sparse)"
+    tm7 = o.SpMatrix.fromListSM(*F.tm7_triples())                                        # "lu (5 x 5 sparse)"
+    for aa in (aa0, tm0, tm7):
+        ok, L, U = _check_lu(o, aa)
+        assert ok
+        assert np.array_equal(np.diag(L), np.ones(L.shape[0]))                           # Doolittle: unit diagonal of L
+    # hand-checked: aa0 = [[1,2],[3,4]] -> L = [[1,0],[3,1]], U = [[1,2],[0,-2]]
+    _, L, U = _check_lu(o, aa0)
+    assert L.tolist() == [[1, 0], [3, 1]] and U.tolist() == [[1, 2], [0, -2]]
+
+
+def test_lu_against_dense_doolittle_and_pivot_error(ora):
+    o = ora
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 30):
+        A = rng.standard_normal((n, n)) * (rng.random((n, n)) < 0.4) + np.diag(rng.uniform(3, 5, n) * n ** 0.5)
+        aa = o.SpMatrix.fromListSM((n, n), [(i, j, A[i, j]) for i in range(n) for j in range(n) if A[i, j] != 0.0])
+        l, u = o.lu(aa)
+        # independent dense Doolittle (no pivoting), same recurrences in numpy
+        L, U = np.eye(n), np.zeros((n, n))
+        for i in range(n):
+            for j in range(i, n):
+                U[i, j] = A[i, j] - L[i, :i] @ U[:i, j]
+            for k in range(i + 1, n):
+                L[k, i] = (A[k, i] - L[k, :i] @ U[:i, i]) / U[i, i]
+        np.testing.assert_allclose(l.toDense(), L, atol=1e-11)
+        np.testing.assert_allclose(u.toDense(), U, atol=1e-11)
+        # ilu0Pre: the same numbers where aa stores something, nothing elsewhere (sparsifyLU)
+        lh, uh = o.ilu0Pre(aa)
+        mask = A != 0.0
+        np.testing.assert_array_equal(lh.toDense(), np.where(mask, l.toDense(), 0.0))
+        np.testing.assert_array_equal(uh.toDense(), np.where(mask, u.toDense(), 0.0))
+        pat = {(i, j) for i in range(n) for j in range(n) if mask[i, j]}
+        for m in (lh, uh):
+            ii, jj, _ = m.toCOO()
+            assert set(zip(ii.tolist(), jj.tolist())) <= pat
+    # a zero pivot: u00 = 0 -> NeedsPivoting at (0,0); a pivot that cancels at step 1
+    with pytest.raises(o.NeedsPivoting) as e:
+        o.lu(o.SpMatrix.fromListSM((2, 2), [(0, 1, 1.0), (1, 0, 1.0)]))
+    assert e.value.row == 0
+    with pytest.raises(o.NeedsPivoting) as e:
+        o.lu(o.SpMatrix.fromListSM((3, 3), [(0, 0, 1.0), (0, 1, 1.0), (1, 0, 1.0), (1, 1, 1.0), (2, 2, 1.0), (2, 1, 1.0)]))
+    assert e.value.row == 1
