@@ -8,7 +8,7 @@
 //     step i   U[i][j] = a_ij - sum_{k<i, l_ik stored, ascending} l_ik u_kj      (j = i .. n-1), kept when isNz
 //              L[k][i] = (a_ki - sum_{q<i, l_kq stored, ascending} l_kq u_qi) / u_ii   (k = i+1 .. n-1), kept when isNz;
 //              a nearZero u_ii with rows left below it raises NeedsPivoting (solveForLij)
-// with __dmul_rn / __dadd_rn / __ddiv_rn (no FMA), hence bit-identical to the oracle's restatement — and it is meant for the
+// with __dmul_rn / __dadd_rn / __ddiv_rn (no FMA), hence bit-identical to the reference's evaluation — and it is meant for the
 // sizes the reference's own algorithm can handle (n <= SLA_LU_MAX_N).  The row sums of a step run in parallel over j (or k);
 // the sum inside each is sequential, as the fold it restates (contractSub, SpMatrix.hs:857-864).
 #include "common.cuh"
