@@ -245,6 +245,56 @@ sla_status sla_dense_to_host(sla_ctx*, const sla_dense*, double* out_colmajor);
 sla_status sla_dense_column(sla_ctx*, const sla_dense* Q, int64_t j, sla_vec** out);   /* column j of the Arnoldi basis as a new vector (extractCol, SpMatrix.hs:329-337) */
 void       sla_dense_free(sla_dense*);
 
+/* ---- one host process, several GPUs ------------------------------------------------------------------------
+ * The reference is a single-threaded pure library; its natural caller is ONE process.  sla_init_multi(n_gpus, device_ids) owns
+ * one context per GPU (a worker thread each) and exposes GLOBAL objects: a matrix is row-partitioned over the GPUs (contiguous
+ * blocks, rows n*p/P), a vector is the concatenation of the ranks' slices; the caller never sees ranks.  Every call below issues
+ * the matching single-rank call on all GPUs at once (those calls are collective: the x exchange and the all-reduced dots of
+ * dist.cu / p2p.cu).  Semantics, error codes and messages are those of the single-GPU entry points above.
+ * (sla_init_dist remains for jobs that already run one process per GPU, e.g. under torchrun.)                                  */
+typedef struct sla_mctx sla_mctx;
+typedef struct sla_mcsr sla_mcsr;
+typedef struct sla_mvec sla_mvec;
+typedef struct sla_mkrylov sla_mkrylov;
+typedef struct sla_mdense sla_mdense;
+sla_status  sla_init_multi(int n_gpus, const int* device_ids /* nullable: 0 .. n_gpus-1 */, sla_mctx** out);
+void        sla_finalize_multi(sla_mctx*);
+const char* sla_multi_last_error(const sla_mctx*);
+int         sla_multi_world(const sla_mctx*);
+sla_ctx*    sla_multi_ctx(sla_mctx*, int rank);            /* the per-GPU context (diagnostics: sla_launch_count, sla_p2p_enabled) */
+sla_status sla_multi_csr_generate(sla_mctx*, int kind, int64_t n, int nnz_per_row, uint64_t seed, int64_t band, sla_mcsr** out);
+sla_status sla_multi_csr_from_csr(sla_mctx*, int64_t m, int64_t n, int64_t nnz, const int32_t* row_ptr, const int32_t* col_idx,
+                                  const double* val, sla_mcsr** out);                      /* global CSR in host memory */
+sla_status sla_multi_csr_dims(const sla_mcsr*, int64_t* m, int64_t* n, int64_t* nnz);
+void       sla_multi_csr_free(sla_mcsr*);
+sla_status sla_multi_vec_create(sla_mctx*, int64_t n, sla_mvec** out);
+sla_status sla_multi_vec_from_host(sla_mctx*, int64_t n, const double* x, sla_mvec** out);
+sla_status sla_multi_vec_generate(sla_mctx*, int64_t n, uint64_t seed, sla_mvec** out);
+sla_status sla_multi_vec_to_host(sla_mctx*, const sla_mvec*, double* x);
+sla_status sla_multi_vec_copy(sla_mctx*, const sla_mvec* src, sla_mvec* dst);
+int64_t    sla_multi_vec_dim(const sla_mvec*);
+void       sla_multi_vec_free(sla_mvec*);
+sla_status sla_multi_spmv(sla_mctx*, const sla_mcsr* A, const sla_mvec* x, sla_mvec* y);                       /* (#>) */
+sla_status sla_multi_dot(sla_mctx*, const sla_mvec* x, const sla_mvec* y, double* out);                        /* (<.>) */
+sla_status sla_multi_norm2(sla_mctx*, const sla_mvec* x, double* out);
+sla_status sla_multi_vec_axpy(sla_mctx*, double a, const sla_mvec* x, const sla_mvec* y, sla_mvec* z);         /* z = y ^+^ (a .* x) */
+sla_status sla_multi_vec_scale(sla_mctx*, double a, const sla_mvec* x, sla_mvec* z);                           /* z = a .* x */
+sla_status sla_multi_bicgstab_init(sla_mctx*, const sla_mcsr* A, const sla_mvec* b, const sla_mvec* x0, sla_mkrylov** st);
+sla_status sla_multi_bicgstab_step(sla_mctx*, const sla_mcsr* A, const sla_mvec* r0hat, sla_mkrylov* st);
+sla_status sla_multi_cgs_init(sla_mctx*, const sla_mcsr* A, const sla_mvec* b, const sla_mvec* x0, sla_mkrylov** st);
+sla_status sla_multi_cgs_step(sla_mctx*, const sla_mcsr* A, const sla_mvec* rhat, sla_mkrylov* st);
+sla_status sla_multi_krylov_clone(sla_mctx*, const sla_mkrylov* st, sla_mkrylov** out);
+sla_status sla_multi_krylov_get(sla_mctx*, const sla_mkrylov*, int field, double* host_out /* n doubles */);
+void       sla_multi_krylov_free(sla_mkrylov*);
+sla_status sla_multi_linsolve0(sla_mctx*, int method /* BICGSTAB_ or CGS_ (CGNE_ needs the distributed transpose: sla_init_dist path) */,
+                               const sla_mcsr* A, const sla_mvec* b, const sla_mvec* x0, const sla_solve_opts*, sla_mvec* x, int* iters,
+                               double* resnorm);
+sla_status sla_multi_gmres(sla_mctx*, const sla_mcsr* A, const sla_mvec* b, const sla_mvec* x0, int restart, const sla_solve_opts*,
+                           sla_mvec* x, int* iters, double* resnorm);
+sla_status sla_multi_arnoldi(sla_mctx*, const sla_mcsr* A, const sla_mvec* b, int kn, sla_mdense** Q, double* h_host, int* nmax);
+sla_status sla_multi_dense_to_host(sla_mctx*, const sla_mdense* Q, double* out_colmajor /* n x (nmax + 1) */);
+void       sla_multi_dense_free(sla_mdense*);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,40 @@ SIGNATURES = {
     "sla_dense_dims": (C.c_int, [_p, _pi64, _pi64]),
     "sla_dense_to_host": (C.c_int, [_p, _p, _pf64]),
     "sla_dense_free": (None, [_p]),
+    # one host process, several GPUs (csrc/multi.cu)
+    "sla_init_multi": (C.c_int, [C.c_int, _pint, _pp]),
+    "sla_finalize_multi": (None, [_p]),
+    "sla_multi_last_error": (C.c_char_p, [_p]),
+    "sla_multi_world": (C.c_int, [_p]),
+    "sla_multi_ctx": (_p, [_p, C.c_int]),
+    "sla_multi_csr_generate": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_uint64, _i64, _pp]),
+    "sla_multi_csr_from_csr": (C.c_int, [_p, _i64, _i64, _i64, _pi32, _pi32, _pf64, _pp]),
+    "sla_multi_csr_dims": (C.c_int, [_p, _pi64, _pi64, _pi64]),
+    "sla_multi_csr_free": (None, [_p]),
+    "sla_multi_vec_create": (C.c_int, [_p, _i64, _pp]),
+    "sla_multi_vec_from_host": (C.c_int, [_p, _i64, _pf64, _pp]),
+    "sla_multi_vec_generate": (C.c_int, [_p, _i64, C.c_uint64, _pp]),
+    "sla_multi_vec_to_host": (C.c_int, [_p, _p, _pf64]),
+    "sla_multi_vec_copy": (C.c_int, [_p, _p, _p]),
+    "sla_multi_vec_dim": (_i64, [_p]),
+    "sla_multi_vec_free": (None, [_p]),
+    "sla_multi_spmv": (C.c_int, [_p, _p, _p, _p]),
+    "sla_multi_dot": (C.c_int, [_p, _p, _p, _pf64]),
+    "sla_multi_norm2": (C.c_int, [_p, _p, _pf64]),
+    "sla_multi_vec_axpy": (C.c_int, [_p, _f64, _p, _p, _p]),
+    "sla_multi_vec_scale": (C.c_int, [_p, _f64, _p, _p]),
+    "sla_multi_bicgstab_init": (C.c_int, [_p, _p, _p, _p, _pp]),
+    "sla_multi_bicgstab_step": (C.c_int, [_p, _p, _p, _p]),
+    "sla_multi_cgs_init": (C.c_int, [_p, _p, _p, _p, _pp]),
+    "sla_multi_cgs_step": (C.c_int, [_p, _p, _p, _p]),
+    "sla_multi_krylov_clone": (C.c_int, [_p, _p, _pp]),
+    "sla_multi_krylov_get": (C.c_int, [_p, _p, C.c_int, _pf64]),
+    "sla_multi_krylov_free": (None, [_p]),
+    "sla_multi_linsolve0": (C.c_int, [_p, C.c_int, _p, _p, _p, _popts, _p, _pint, _pf64]),
+    "sla_multi_gmres": (C.c_int, [_p, _p, _p, _p, C.c_int, _popts, _p, _pint, _pf64]),
+    "sla_multi_arnoldi": (C.c_int, [_p, _p, _p, C.c_int, _pp, _pf64, _pint]),
+    "sla_multi_dense_to_host": (C.c_int, [_p, _p, _pf64]),
+    "sla_multi_dense_free": (None, [_p]),
 }
 
 

@@ -428,6 +428,8 @@ bool sla_p2p_active(const sla_ctx* c);
 sla_status sla_p2p_allreduce(sla_ctx* c, int nv, int src, int fin, int dst);
 sla_status sla_p2p_check(sla_ctx* c);
 void sla_p2p_free(sla_ctx* c);
+void* sla_p2p_window(sla_ctx* c);                                                                 // multi.cu: one process, several GPUs
+sla_status sla_p2p_attach_direct(sla_ctx* c, void* const* wins);
 bool sla_xwin_active(const sla_csr* A);
 int sla_xwin_mode(const sla_csr* A);                                                             // 0 off, 1 push kernel, 2 arrival order, 3 LL halo, 4 copy-engine all-gather
 sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_local);

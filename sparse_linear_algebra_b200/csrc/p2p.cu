@@ -40,6 +40,7 @@ struct p2p_item { int peer; int len; int64_t goff; int64_t src; };
 
 struct sla_p2p {                                 // per context: the all-reduce window
   int enabled;
+  int direct;                                    // peers are plain device pointers of THIS process (sla_init_multi), not IPC mappings
   char* win;
   char* peer[SLA_MAX_WORLD];
   char** d_peer;
@@ -179,9 +180,9 @@ sla_status open_peers(sla_ctx* c, const void* handles, char* own, char** peer) {
   return SLA_OK;
 }
 
-void close_peers(sla_ctx* c, char** peer) {
+void close_peers(sla_ctx* c, char** peer, bool direct = false) {
   for (int p = 0; p < c->world; ++p) {
-    if (p != c->rank && peer[p]) cudaIpcCloseMemHandle(peer[p]);
+    if (p != c->rank && peer[p] && !direct) cudaIpcCloseMemHandle(peer[p]);
     peer[p] = nullptr;
   }
 }
@@ -220,6 +221,19 @@ extern "C" sla_status sla_p2p_attach(sla_ctx* c, const void* handles) {
   if (!c || !handles || !c->p2p) return SLA_ERR_INVALID;
   sla_p2p* P = c->p2p;
   SLA_TRY(open_peers(c, handles, P->win, P->peer));
+  SLA_CUDA(c, cudaMemcpyAsync(P->d_peer, P->peer, sizeof(char*) * SLA_MAX_WORLD, cudaMemcpyHostToDevice, c->stream));
+  SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SLA_OK;
+}
+
+// One process driving several GPUs (multi.cu): the windows of the other ranks are ordinary device pointers of this process,
+// reachable once peer access is enabled — no IPC handles.  wins: world pointers in rank order (own entry ignored).
+void* sla_p2p_window(sla_ctx* c) { return c->p2p ? (void*)c->p2p->win : nullptr; }
+sla_status sla_p2p_attach_direct(sla_ctx* c, void* const* wins) {
+  if (!c || !wins || !c->p2p) return SLA_ERR_INVALID;
+  sla_p2p* P = c->p2p;
+  for (int p = 0; p < c->world; ++p) P->peer[p] = p == c->rank ? P->win : (char*)wins[p];
+  P->direct = 1;
   SLA_CUDA(c, cudaMemcpyAsync(P->d_peer, P->peer, sizeof(char*) * SLA_MAX_WORLD, cudaMemcpyHostToDevice, c->stream));
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));
   return SLA_OK;
@@ -274,7 +288,7 @@ sla_status sla_p2p_check(sla_ctx* c) {
 void sla_p2p_free(sla_ctx* c) {
   sla_p2p* P = c->p2p;
   if (!P) return;
-  close_peers(c, P->peer);
+  close_peers(c, P->peer, P->direct != 0);
   cudaFree(P->win); cudaFree(P->d_peer); cudaFree(P->d_err); cudaFreeHost(P->h_err);
   delete P;
   c->p2p = nullptr;

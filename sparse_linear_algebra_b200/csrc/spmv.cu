@@ -679,9 +679,9 @@ struct SpmvArgs {
 
 template <int EPI, bool ACC, int DIST>
 static sla_status launch_one(sla_ctx* c, const SpmvArgs& a) {
-  static int carve_set = 0;
-  if (!carve_set) {
-    carve_set = 1;
+  static char carve_set[64] = {0};          // function attributes are per device (one process may drive several GPUs)
+  if (!carve_set[c->device & 63]) {
+    carve_set[c->device & 63] = 1;
     if (const char* e = getenv("SLA_SPMV_CARVEOUT"))
       cudaFuncSetAttribute(spmv_tile_kernel<SLA_SPMV_TILE, EPI, ACC, DIST, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
   }
@@ -689,9 +689,9 @@ static sla_status launch_one(sla_ctx* c, const SpmvArgs& a) {
   if (c->spmv_tma) {
     // TMA-staged persistent variant: SPMV_CTAS_PER_SM CTAs per SM, each looping over tiles
     constexpr size_t smem = (size_t)SPMV_STAGES * SLA_SPMV_TILE * 12 + (size_t)(SLA_SPMV_TILE + SLA_SPMV_TILE / 8) * 8;
-    static int attr_set = 0;
-    if (!attr_set) {
-      attr_set = 1;
+    static char attr_set[64] = {0};
+    if (!attr_set[c->device & 63]) {
+      attr_set[c->device & 63] = 1;
       SLA_CUDA(c, cudaFuncSetAttribute(spmv_tma_kernel<SLA_SPMV_TILE, EPI, ACC, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     nblk = a.ntiles < SLA_NUM_SMS * c->spmv_tma ? a.ntiles : SLA_NUM_SMS * c->spmv_tma;
