@@ -534,8 +534,8 @@ def run_gpu(args):
             C5 = sla.DenseMatrix.zeros(n, k5, sla.BF16)
             for tag, kind in (("k16", sla.GEN_BLOCK16), ("uniform", sla.GEN_UNIFORM)):
                 A5 = sla.SpMatrix.generate(kind, n, 32, 0x5EED0005)
-                reps = 5 if tag == "k16" else 2
-                ms5, _ = timed(lambda: A5.matMat(B5, out=C5), reps, 1)
+                reps = 10 if tag == "k16" else 2
+                ms5, _ = timed(lambda: A5.matMat(B5, out=C5), reps, 3 if tag == "k16" else 1)
                 b5 = 6 * A5.nnz + 4 * (n + 1) + 4 * n * k5        # B_spmm, SURVEY.md §8(d): bf16 A values, B and C once
                 extra[f"spmm_cfg5_{tag}_ms"] = ms5
                 extra[f"spmm_cfg5_{tag}_gbs"] = b5 / (ms5 * 1e-3) / 1e9
@@ -554,7 +554,7 @@ def run_gpu(args):
                 m5 = s5[rank + 1] - s5[rank]
                 B5 = sla.DenseMatrix.generate(m5, k5, 0x5EED0055 + rank, sla.BF16)      # this rank's row slice of B
                 C5 = sla.DenseMatrix.zeros(m5, k5, sla.BF16)
-                ms5, _ = timed(lambda: A5.matMat(B5, out=C5), 5, 1)
+                ms5, _ = timed(lambda: A5.matMat(B5, out=C5), 10, 3)
                 b5 = 6 * n * 32 + 4 * (n + 1) + 4 * n * k5
                 extra["spmm_cfg5_k16_dist_ms"] = ms5
                 extra["spmm_cfg5_k16_dist_gbs"] = b5 / (ms5 * 1e-3) / 1e9

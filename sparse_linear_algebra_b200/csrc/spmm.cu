@@ -410,6 +410,258 @@ spmm_bsr_tc_kernel(const int* __restrict__ brow_ptr, const int* __restrict__ bco
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
 }
 
+// =================================================================================================================
+// Pipelined tile path (the default): the same product as spmm_bsr_tc_kernel, fed by TMA and warp-specialised.
+//
+//   warp 0      TMA producer   one lane issues, per 16 x 16 block of A, ONE cp.async.bulk.tensor (SASS UTMALDG) for the 16 x 128
+//                              slab of B it multiplies — B is described to the TMA unit as a 3-D tensor (64 columns, rows, 2 column
+//                              halves) with SWIZZLE_128B, so the 4 KB land directly in the MN-major 128-byte-swizzled canonical
+//                              layout tcgen05.mma reads (two 64-column groups 2 KB apart = LBO, 8-row groups 1 KB apart = SBO) —
+//                              and one 512-byte bulk copy (UBLKCP) for the block of A, into a ring of TC_RING stages guarded by
+//                              full / empty mbarriers; the 32 lanes fetch the block-column indices of the next 32 blocks at once
+//   warp 1      MMA issuer     waits for a stage, issues tcgen05.mma (M128 N16 K16, bf16 -> fp32 in TMEM) and commits the stage's
+//                              `empty` barrier; the accumulator is double-buffered in TMEM (2 x 16 columns): after the last block
+//                              of a block row it commits `tmem_full` and starts the next row in the other half
+//   warps 2-5   epilogue       tcgen05.ld their TMEM lane quarter, release the accumulator, convert to bf16 into a double-buffered
+//                              16 x 128 shared-memory tile and hand it to the TMA unit (cp.async.bulk.tensor store, SASS UTMASTG)
+// so that loads, MMAs and stores of different block rows overlap inside one CTA; CTAs own CONTIGUOUS ranges of block rows
+// (the producer and the issuer walk brow_ptr / bcol as plain sequential streams).  Every wait is bounded: a protocol error
+// traps instead of hanging the GPU.
+#include <cuda.h>
+
+#define TC_RING 8
+#define TCP_THREADS 192
+#define TCP_SLAB_BYTES 4096
+#define TCP_ABLK_BYTES 512
+#define TCP_CT_BYTES 4096
+#define TCP_SMEM_BYTES (TC_RING * (TCP_SLAB_BYTES + TCP_ABLK_BYTES) + 2 * TCP_CT_BYTES + 1024)
+#define TCP_SPIN_LIMIT 4000000000LL     // ~2 s of SM clocks
+
+__device__ __forceinline__ void tcp_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(spmm_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tcp_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = spmm_smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > TCP_SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tcp_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(spmm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcp_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(spmm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // as umma_desc, with layout_type = SWIZZLE_128B (2) at [61,64); the operand is 1024-byte aligned, so base_offset = 0
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) |
+         (1ULL << 46) | (2ULL << 61);
+}
+
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+spmm_bsr_tc_pipe_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const int* __restrict__ brow_ptr,
+                        const int* __restrict__ bcol, const __nv_bfloat16* __restrict__ bval, int nbr, int rows_per_cta) {
+  extern __shared__ unsigned char tcp_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tcp_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* slab = base;                                           // TC_RING x 4 KB, each 1024-byte aligned (swizzle atoms)
+  unsigned char* ablk = base + TC_RING * TCP_SLAB_BYTES;                // TC_RING x 512 B
+  unsigned char* ctile = ablk + TC_RING * TCP_ABLK_BYTES;               // 2 x 4 KB
+  __shared__ __align__(8) uint64_t full_bar[TC_RING], empty_bar[TC_RING], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(nbr, r0 + rows_per_cta);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(spmm_smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < TC_RING; ++s) { tcp_mbar_init(&full_bar[s], 1); tcp_mbar_init(&empty_bar[s], 1); }
+    tcp_mbar_init(&tfull_bar[0], 1); tcp_mbar_init(&tfull_bar[1], 1);
+    tcp_mbar_init(&tempty_bar[0], 128); tcp_mbar_init(&tempty_bar[1], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (r0 < r1) {
+    if (warp == 0) {
+      // ===== TMA producer =====
+      const int b_begin = brow_ptr[r0], b_end = brow_ptr[r1];
+      uint32_t stage = 0, phase = 0;
+      for (int b0 = b_begin; b0 < b_end; b0 += 32) {
+        const int mine = b0 + lane < b_end ? bcol[b0 + lane] : 0;
+        const int cnt = min(32, b_end - b0);
+        for (int j = 0; j < cnt; ++j) {
+          const int bc = __shfl_sync(0xffffffffu, mine, j);
+          if (lane == 0) {
+            tcp_mbar_wait(&empty_bar[stage], phase ^ 1u);
+            tcp_mbar_expect_tx(&full_bar[stage], TCP_SLAB_BYTES + TCP_ABLK_BYTES);
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(spmm_smem_u32(slab + stage * TCP_SLAB_BYTES)), "l"(&tmB), "r"(spmm_smem_u32(&full_bar[stage])),
+                           "r"(0), "r"(bc * 16), "r"(0) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(spmm_smem_u32(ablk + stage * TCP_ABLK_BYTES)), "l"(bval + (size_t)(b0 + j) * 256), "r"(TCP_ABLK_BYTES),
+                           "r"(spmm_smem_u32(&full_bar[stage])) : "memory");
+          }
+          if (++stage == TC_RING) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer =====
+      // kind::f16 instruction descriptor: D = F32, A = B = BF16, A MN-major, B K-major, N = 16, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int rb = r0; rb < r1; rb += 32) {
+        const int rr = rb + lane;
+        const int my_s = rr < r1 ? brow_ptr[rr] : 0, my_e = rr < r1 ? brow_ptr[rr + 1] : 0;
+        const int cnt = min(32, r1 - rb);
+        for (int q = 0; q < cnt; ++q) {
+          const int nb = __shfl_sync(0xffffffffu, my_e, q) - __shfl_sync(0xffffffffu, my_s, q);
+          if (nb == 0) continue;
+          if (lane == 0) tcp_mbar_wait(&tempty_bar[as], aphase ^ 1u);        // the epilogue has drained this half of the accumulator
+          __syncwarp();
+          for (int j = 0; j < nb; ++j) {
+            if (lane == 0) {
+              tcp_mbar_wait(&full_bar[stage], phase);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint64_t adesc = umma_desc_sw128(spmm_smem_u32(slab + stage * TCP_SLAB_BYTES), 2048, 1024);
+              const uint64_t bdesc = umma_desc(spmm_smem_u32(ablk + stage * TCP_ABLK_BYTES), 128, 256);
+              const uint32_t acc = j > 0 ? 1u : 0u;
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                  ::"r"(tmem + as * 16u), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+              // the stage may be refilled once this MMA (and everything before it) has read its operands
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(spmm_smem_u32(&empty_bar[stage])) : "memory");
+              if (j + 1 == nb)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(spmm_smem_u32(&tfull_bar[as])) : "memory");
+            }
+            __syncwarp();
+            if (++stage == TC_RING) { stage = 0; phase ^= 1u; }
+          }
+          as ^= 1u;
+          if (as == 0) aphase ^= 1u;
+        }
+      }
+    } else {
+      // ===== epilogue: 128 threads, thread = column of C =====
+      const int q4 = warp & 3;                                   // the TMEM lane quarter this warp may read
+      const int ccol = q4 * 32 + lane;
+      const bool leader = tid == 64;
+      uint32_t as = 0, aphase = 0;
+      int it = 0;
+      for (int br = r0; br < r1; ++br, ++it) {
+        const int nb = brow_ptr[br + 1] - brow_ptr[br];
+        uint32_t r[16];
+        if (nb > 0) {
+          tcp_mbar_wait(&tfull_bar[as], aphase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + as * 16u;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          tcp_mbar_arrive(&tempty_bar[as]);                      // this half of the accumulator may be overwritten
+          as ^= 1u;
+          if (as == 0) aphase ^= 1u;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = 0u;
+        }
+        __nv_bfloat16* ct = reinterpret_cast<__nv_bfloat16*>(ctile + (it & 1) * TCP_CT_BYTES);
+        // the TMA store that read this tile two rows ago must be done with it
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ct[i * 128 + ccol] = __float2bfloat16_rn(__uint_as_float(r[i]));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&tmC), "r"(spmm_smem_u32(ct)), "r"(0), "r"(br * 16) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+}
+
+typedef CUresult (*sla_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static sla_encode_tiled_fn get_encode_tiled() {
+  static sla_encode_tiled_fn fn = nullptr;
+  static int tried = 0;
+  if (!tried) {
+    tried = 1;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (sla_encode_tiled_fn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// returns SLA_ERR_INVALID when the pipelined kernel cannot be set up (the caller falls back to spmm_bsr_tc_kernel)
+static sla_status spmm_bsr_tc_pipe(sla_ctx* c, const sla_csr* A, const sla_dense* B, sla_dense* C) {
+  sla_encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return SLA_ERR_INVALID;
+  if (((uintptr_t)B->d & 15u) || ((uintptr_t)C->d & 15u)) return SLA_ERR_INVALID;
+  CUtensorMap tmB, tmC;
+  {
+    // B (rows x 128 bf16, row-major) as (64 columns, rows, 2 column halves): one box = a 16-row slab, half by half
+    const cuuint64_t dims[3] = {64, (cuuint64_t)B->rows, 2};
+    const cuuint64_t strides[2] = {256, 128};                   // bytes: next row, next column half
+    const cuuint32_t box[3] = {64, 16, 2}, es[3] = {1, 1, 1};
+    if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)B->d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return SLA_ERR_INVALID;
+  }
+  {
+    const cuuint64_t dims[2] = {128, (cuuint64_t)C->rows};
+    const cuuint64_t strides[1] = {256};
+    const cuuint32_t box[2] = {128, 16}, es[2] = {1, 1};
+    if (enc(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)C->d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return SLA_ERR_INVALID;
+  }
+  static char attr_set[64] = {0};
+  if (!attr_set[c->device & 63]) {
+    if (cudaFuncSetAttribute(spmm_bsr_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return SLA_ERR_INVALID; }
+    attr_set[c->device & 63] = 1;
+  }
+  int per_sm = 4;                     // measured on cfg 5 K16: 2 -> 1.84 ms, 3 -> 1.362, 4 -> 1.356, 6 -> 1.52 (profiles/r02_spmm_pipe_ab.txt)
+  if (const char* e = getenv("SLA_SPMM_TC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+  int grid = SLA_NUM_SMS * per_sm;
+  if (grid > A->bsr_nbr) grid = A->bsr_nbr;
+  if (grid < 1) grid = 1;
+  const int rows_per_cta = (A->bsr_nbr + grid - 1) / grid;
+  grid = (A->bsr_nbr + rows_per_cta - 1) / rows_per_cta;
+  spmm_bsr_tc_pipe_kernel<<<grid, TCP_THREADS, TCP_SMEM_BYTES, c->stream>>>(tmB, tmC, A->bsr_row_ptr, A->bsr_col, (const __nv_bfloat16*)A->bsr_val,
+                                                                           A->bsr_nbr, rows_per_cta);
+  SLA_LAUNCH_CHECK(c);
+  return SLA_OK;
+}
+
 // Builds the BSR copy of A on first use; returns the fill ratio nnz / (16*16*nblocks) through *fill.
 static sla_status ensure_bsr(sla_ctx* c, const sla_csr* A, double* fill) {
   sla_csr* Am = const_cast<sla_csr*>(A);
@@ -454,6 +706,12 @@ sla_status sla_spmm_bsr_tc(sla_ctx* c, const sla_csr* A, const sla_dense* B, sla
   double fill = 0;
   SLA_TRY(ensure_bsr(c, A, &fill));
   if (fill < min_fill) return SLA_ERR_INVALID;
+  // the TMA-fed warp-specialised pipeline is the default; SLA_SPMM_TC_PIPE=0 selects the one-stage kernel it replaced
+  const char* pipe = getenv("SLA_SPMM_TC_PIPE");
+  if (!(pipe && atoi(pipe) == 0)) {
+    const sla_status ps = spmm_bsr_tc_pipe(c, A, B, C);
+    if (ps != SLA_ERR_INVALID) return ps;
+  }
   int grid = A->bsr_nbr < SLA_NUM_SMS * 16 ? A->bsr_nbr : SLA_NUM_SMS * 16;
   if (grid < 1) grid = 1;
   spmm_bsr_tc_kernel<<<grid, 128, 0, c->stream>>>(A->bsr_row_ptr, A->bsr_col, (const __nv_bfloat16*)A->bsr_val,

@@ -545,12 +545,15 @@ def _spmm_bound_check(A, Bh, C):
     assert np.array_equal(C, _bf16_round(C))
 
 
-@pytest.mark.parametrize("m,n,nblocks,fill", [(16, 16, 1, 1.0), (64, 64, 6, 1.0), (160, 4096, 60, 0.6), (1000, 2000, 400, 1.0)])
-def test_spmm_tensor_core_path(sla, monkeypatch, m, n, nblocks, fill):
+@pytest.mark.parametrize("pipe", ["1", "0"])
+@pytest.mark.parametrize("m,n,nblocks,fill", [(16, 16, 1, 1.0), (64, 64, 6, 1.0), (160, 4096, 60, 0.6), (1000, 2000, 400, 1.0), (40000, 8192, 30000, 0.9)])
+def test_spmm_tensor_core_path(sla, monkeypatch, m, n, nblocks, fill, pipe):
     """The tcgen05 / TMEM tile path (16 x 16 bf16 blocks, M128 N16 K16 MMAs, fp32 accumulators) on block-structured
-    matrices, forced with SLA_SPMM_TC=1: same bound as the gather kernel; includes a ragged last block row and
-    partially filled blocks (zero-padded)."""
+    matrices, forced with SLA_SPMM_TC=1: same bound as the gather kernel; includes a ragged last block row, empty block
+    rows and partially filled blocks (zero-padded).  pipe = 1: the TMA-fed warp-specialised pipeline (default);
+    pipe = 0: the one-stage kernel it replaced."""
     monkeypatch.setenv("SLA_SPMM_TC", "1")
+    monkeypatch.setenv("SLA_SPMM_TC_PIPE", pipe)
     rng = np.random.default_rng(m + n)
     nbr, nbc = (m + 15) // 16, n // 16
     ii, jj = [], []
