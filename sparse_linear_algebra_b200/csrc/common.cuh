@@ -106,6 +106,7 @@ struct sla_csr {
   int panel_width;           // columns per panel
   sla_panel* panels;         // host array of device pointers
   sla_dist_info* dist;       // non-null: this is the local row block of a distributed matrix (n = GLOBAL columns)
+  void* band;                // sla_band_plan (spmv_band.cuh): the matrix re-sorted for the x-in-shared-memory kernel, null when not banded
   void* val_bf16;            // bf16 copy of val for the bf16 (##) path, built on first use (spmm.cu)
   int bsr_ready, bsr_nbr, bsr_nblk; int *bsr_row_ptr, *bsr_col; void* bsr_val;   // 16 x 16 bf16 block copy for the tcgen05 (##) path
   int chunk_ready, chunk_tile[8], chunk_row[8];   // row chunks of the last pass for the pipelined host (#>)
@@ -407,6 +408,7 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
 sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A);
 sla_status sla_spmv_host_pipelined(sla_ctx* c, const sla_csr* A, const double* x_host, double* y_host, double* dx, double* dy);
 void sla_csr_free_panels(sla_csr* A);
+void sla_csr_free_band(sla_csr* A);
 sla_status sla_csr_alloc(sla_ctx* c, int64_t m, int64_t n, int64_t nnz, sla_csr** out);
 sla_status sla_vec_alloc(sla_ctx* c, int64_t n, sla_vec** out);
 sla_status sla_read_scalars(sla_ctx* c, int first, int count, double* host_out);

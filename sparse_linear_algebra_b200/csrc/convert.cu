@@ -51,6 +51,7 @@ extern "C" void sla_csr_free(sla_csr* A) {
   if (A->ctx) cudaStreamSynchronize(A->ctx->stream);
   if (A->T) sla_csr_free(A->T);
   sla_csr_free_panels(A);
+  sla_csr_free_band(A);
   sla_csr_free_dist(A);
   sla_csr_free_bsr(A);
   sla_csr_free_tri(A);

@@ -28,7 +28,10 @@
 // result stays bit-identical — while every pass gathers from an L2-resident slice of x.
 #include "common.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <new>
+#include <vector>
 #include <stdlib.h>
 
 #define SLA_LONG_ROW 256
@@ -120,6 +123,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// the same wait with a watchdog: a protocol error traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -592,6 +607,8 @@ static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
   return s;
 }
 
+static sla_status build_band_plan(sla_ctx* c, sla_csr* A);      // spmv_band.cuh: x staged through shared memory for matrices with column locality
+
 // Builds the tile plan, picks the gather cache policy and, when x cannot stay L2-resident and the matrix has
 // no column locality, the column-panel copy.
 //   SLA_SPMV_PANELS=1 disables panels, =P (>1) forces P panels, unset/0 = automatic.
@@ -603,6 +620,7 @@ sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
   sla_csr_free_panels(A);
   A->hints = c->spmv_hints & 3;
   if (A->nnz == 0 || A->m == 0) return SLA_OK;
+  SLA_TRY(build_band_plan(c, A));
   // how wide a stretch of x does one CTA gather from, on average?
   double mean_span_bytes = 0.0;
   {
@@ -626,6 +644,7 @@ sla_status sla_csr_build_plan(sla_ctx* c, sla_csr* A) {
   int want = 0;
   if (const char* e = getenv("SLA_SPMV_PANELS")) want = atoi(e);
   if (want == 1) return SLA_OK;
+  if (A->band && want == 0) return SLA_OK;          // the band plan keeps x in shared memory: no column panels needed
   if (want == 0) {
     if ((uint64_t)A->n * 8u <= SLA_PANEL_MIN_X || mean_span_bytes <= (double)SLA_PANEL_MIN_SPAN) return SLA_OK;
     want = (int)(((uint64_t)A->n * 8u + SLA_PANEL_BYTES - 1) / SLA_PANEL_BYTES);
@@ -666,6 +685,8 @@ partials_reduce_kernel(const double* __restrict__ partials, int nblk, double* pa
   __syncthreads();
   grid_reduce_finish<2>(acc, partials2, counter, scal, fin, dst, red, pa);
 }
+
+#include "spmv_band.cuh"
 
 // everything one launch needs besides the epilogue selection
 struct SpmvArgs {
@@ -780,6 +801,7 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   (void)u1;
   if (A->ntiles > SLA_MAX_PARTIALS) return sla_fail(c, SLA_ERR_INVALID, "spmv: matrix has too many tiles");
   const bool dist = A->dist != nullptr;
+  if (A->band && !dist) return band_launch(c, A, x, y, epi, u0, fin, dst);
   if (dist && c->world > 1 && sla_xwin_mode(A) == 2 && A->npanels == c->world && A->m > 0)
     return spmv_launch_arrival(c, A, x, y, epi, u0, fin, dst);
   // mode 4: the same copy-engine all-gather, waited for as a whole, then the matrix's own plan (no per-source panels)

@@ -774,3 +774,60 @@ def test_spmv_bulk_staging_bit_exact(sla, o, monkeypatch):
         assert xs[0].tobytes() == xs[1].tobytes()
     finally:
         ctx.set_option("spmv_bulk", int(__import__("os").environ.get("SLA_SPMV_BULK", "0")))
+
+
+# =============================================================== round 2: x staged through shared memory (band plan, spmv_band.cuh)
+
+@pytest.mark.parametrize("R,W", [("64", "32"), ("16", "16"), ("4096", "1024"), ("8192", "4096")])
+def test_spmv_band_plan_bit_exact(sla, o, monkeypatch, R, W):
+    """The band plan (row blocks x column sub-panels, x in shared memory, SLA_SPMV_BAND=1 forces it at any size) gives the
+    same bits as the oracle's left fold: banded, stencil, a narrow random matrix with empty rows, long rows (any length is
+    exact here), ragged sizes, odd n; with the Krylov epilogues riding on it (dots: tolerance, another reduction grid)."""
+    monkeypatch.setenv("SLA_SPMV_BAND", "1")
+    monkeypatch.setenv("SLA_BAND_R", R)
+    monkeypatch.setenv("SLA_BAND_W", W)
+    seed = 0x5EED0051
+    cases = [(sla.GEN_BANDED, o.GEN_BANDED, 30001, 16, 300), (sla.GEN_LAPLACE2D, o.GEN_LAPLACE2D, 97 * 97, 5, 97),
+             (sla.GEN_BANDED, o.GEN_BANDED, 5000, 8, 7)]
+    for gk, ok_, n, k, band in cases:
+        A = sla.SpMatrix.generate(gk, n, k, seed, band)
+        Ao = o.SpMatrix.synth(ok_, n, k, seed, band)
+        x = sla.SpVector.generate(n, seed + 1)
+        xo = o.SpVector.synth(seed + 1, n)
+        assert (A @ x).toDenseListSV().tobytes() == Ao.matVec(xo).toDenseListSV().tobytes(), (gk, n, R, W)
+    # hand-made: empty rows, one row of 900 entries inside a 1000-column window, a dense-ish cluster, odd dimensions
+    rng = np.random.default_rng(11)
+    m, n = 2501, 3001
+    ii, jj = [], []
+    for r in range(m):
+        if r % 7 == 3:
+            continue                                                     # empty row
+        width = 900 if r == 1200 else int(rng.integers(1, 12))
+        lo = max(0, min(n - 1000, r - 500))
+        cols = rng.choice(1000, size=width, replace=False) + lo
+        ii.append(np.full(width, r)); jj.append(cols)
+    i, j = np.concatenate(ii), np.concatenate(jj)
+    v = rng.standard_normal(i.size)
+    A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+    Ao = o.SpMatrix.fromCOO((m, n), i, j, v)
+    xh = rng.standard_normal(n)
+    y = (A @ sla.SpVector.mkSpVR(n, xh)).toDenseListSV()
+    yo = Ao.matVec(o.SpVector.mkSpVR(n, xh)).toDenseListSV()
+    assert y.tobytes() == yo.tobytes()
+    # a BiCGSTAB trajectory on the banded family: same bits with and without the band plan
+    n, k = 20000, 12
+    xs = []
+    for bandplan in ("1", "0"):
+        monkeypatch.setenv("SLA_SPMV_BAND", bandplan)
+        A = sla.SpMatrix.generate(sla.GEN_BANDED, n, k, seed, 200)
+        b = A @ sla.SpVector.generate(n, seed + 2)
+        st = sla.bicgsInit(A, b, sla.SpVector.zeroSV(n))
+        rhat = st.r.copy()
+        for _ in range(5):
+            sla.bicgstabStep(A, rhat, st)
+        xs.append(st.x.toDenseListSV())
+        xsol, its, res = sla.linSolve0(sla.BICGSTAB_, A, b, sla.SpVector.constv(n, 0.1), info=True)
+        xs.append(np.array([its, res]))
+    # (#>) is bit-identical either way; the fused dots are reduced over a different grid, so the iterates agree to rounding
+    np.testing.assert_allclose(xs[0], xs[2], rtol=1e-10, atol=1e-13)
+    assert xs[1][0] == xs[3][0] and abs(xs[1][1] - xs[3][1]) <= 1e-8 * max(abs(xs[3][1]), 1e-300)
