@@ -36,17 +36,27 @@ static sla_status ctx_create(int device, int rank, int world, sla_ctx** out) {
   if (const char* h = getenv("SLA_SPMV_HINTS")) c->spmv_hints = atoi(h);
   if (const char* h = getenv("SLA_SPMV_TMA")) c->spmv_tma = atoi(h);
   if (const char* h = getenv("SLA_SPMV_BULK")) c->spmv_bulk = atoi(h);
-  SLA_CUDA(c, cudaSetDevice(device));
-  SLA_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  SLA_CUDA(c, cudaEventCreate(&c->ev0));
-  SLA_CUDA(c, cudaEventCreate(&c->ev1));
-  SLA_CUDA(c, cudaMalloc(&c->scal, sizeof(double) * SLA_SCAL_SLOTS));
-  SLA_CUDA(c, cudaMemsetAsync(c->scal, 0, sizeof(double) * SLA_SCAL_SLOTS, c->stream));
-  SLA_CUDA(c, cudaMalloc(&c->partials, sizeof(double) * 4 * (size_t)SLA_MAX_PARTIALS));
-  SLA_CUDA(c, cudaMalloc(&c->counter, sizeof(unsigned int) * 4));
-  SLA_CUDA(c, cudaMemsetAsync(c->counter, 0, sizeof(unsigned int) * 4, c->stream));
-  SLA_CUDA(c, cudaMallocHost(&c->h_scal, sizeof(double) * SLA_SCAL_SLOTS));
-  SLA_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev1);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->scal, sizeof(double) * SLA_SCAL_SLOTS);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(c->scal, 0, sizeof(double) * SLA_SCAL_SLOTS, c->stream);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->partials, sizeof(double) * 4 * (size_t)SLA_MAX_PARTIALS);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->counter, sizeof(unsigned int) * 4);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(c->counter, 0, sizeof(unsigned int) * 4, c->stream);
+  if (ce == cudaSuccess) ce = cudaMallocHost(&c->h_scal, sizeof(double) * SLA_SCAL_SLOTS);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+  if (ce != cudaSuccess) {                        // nothing of a half-built context survives
+    snprintf(g_init_err, sizeof(g_init_err), "sla_init: CUDA error %s while creating the context on device %d", cudaGetErrorString(ce), device);
+    cudaGetLastError();
+    cudaFree(c->scal); cudaFree(c->partials); cudaFree(c->counter); cudaFreeHost(c->h_scal);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SLA_ERR_CUDA;
+  }
   *out = c;
   return SLA_OK;
 }
@@ -132,6 +142,7 @@ extern "C" sla_status sla_timer_stop(sla_ctx* c, float* ms) {
 }
 
 sla_status sla_read_scalars(sla_ctx* c, int first, int count, double* host_out) {
+  SLA_GUARD(c);
   SLA_CUDA(c, cudaMemcpyAsync(c->h_scal + first, c->scal + first, sizeof(double) * (size_t)count,
                               cudaMemcpyDeviceToHost, c->stream));
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -143,6 +154,7 @@ sla_status sla_read_scalars(sla_ctx* c, int first, int count, double* host_out) 
 
 sla_status sla_vec_alloc(sla_ctx* c, int64_t n, sla_vec** out) {
   if (!c || !out || n < 0) return SLA_ERR_INVALID;
+  SLA_GUARD(c);
   sla_vec* v = new (std::nothrow) sla_vec();
   if (!v) return sla_fail(c, SLA_ERR_ALLOC, "vec alloc");
   v->ctx = c; v->n = n; v->version = ++c->stamp; v->owns = true; v->d = nullptr;
@@ -219,6 +231,7 @@ static sla_status check3(sla_ctx* c, const sla_vec* x, const sla_vec* y, const s
 
 extern "C" sla_status sla_spmv(sla_ctx* c, const sla_csr* A, const sla_vec* x, sla_vec* y) {
   if (!c || !A || !x || !y) return SLA_ERR_INVALID;
+  SLA_GUARD(c);
   if (csr_xdim(A) != x->n) {   // matVecSD | nc == n ... | otherwise = error   Common.hs:248-250
     snprintf(c->err, sizeof(c->err), "matVec : mismatched dimensions (%lld,%lld)", (long long)csr_xdim(A), (long long)x->n);
     return SLA_ERR_SIZE_MISMATCH;
@@ -325,6 +338,7 @@ static sla_status scratch_vec(sla_ctx* c, sla_vec** slot, int64_t n) {
 // Device staging vectors are cached in the ctx, so a steady-state call does no allocation.
 extern "C" sla_status sla_spmv_host(sla_ctx* c, const sla_csr* A, const double* x_host, double* y_host) {
   if (!c || !A || !x_host || !y_host) return SLA_ERR_INVALID;
+  SLA_GUARD(c);
   SLA_TRY(scratch_vec(c, &c->scratch_x, csr_xdim(A)));
   SLA_TRY(scratch_vec(c, &c->scratch_y, A->m));
   if (!A->dist && !c->spmv_tma && A->m > 0 && !getenv("SLA_HOST_NO_PIPELINE"))

@@ -59,6 +59,7 @@ ew_kernel(OP op, int64_t n, Ptrs<OP::NIN> in, Ptrs<OP::NOUT> out, double* scal, 
 template <class OP>
 static inline sla_status ew_launch(sla_ctx* c, OP op, int64_t n, Ptrs<OP::NIN> in, Ptrs<OP::NOUT> out,
                                    int fin = FIN_STORE, int dst = S_TMP0) {
+  SLA_GUARD(c);
   int64_t blocks = ((n >> 1) + EW_THREADS - 1) / EW_THREADS;
   if (blocks < 1) blocks = 1;
   if (blocks > EW_MAX_BLOCKS) blocks = EW_MAX_BLOCKS;

@@ -156,6 +156,10 @@ static inline sla_status sla_fail(sla_ctx* c, sla_status s, const char* msg) {
     }                                                                                        \
   } while (0)
 
+// The current device is per host thread and other code in the process (torch, another context) may change it: entry points that
+// allocate or launch re-select the context's device first (a thread-local no-op when it is already current).
+#define SLA_GUARD(ctx) do { if (ctx) cudaSetDevice((ctx)->device); } while (0)
+
 #define SLA_TRY(call)                       \
   do {                                      \
     sla_status _s = (call);                 \

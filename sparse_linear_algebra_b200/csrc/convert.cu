@@ -19,6 +19,7 @@ static int64_t padded_nnz(int64_t nnz) {
 
 sla_status sla_csr_alloc(sla_ctx* c, int64_t m, int64_t n, int64_t nnz, sla_csr** out) {
   if (!c || !out || m < 0 || n < 0 || nnz < 0) return SLA_ERR_INVALID;
+  SLA_GUARD(c);
   if (m >= (1LL << 31) - 1 || n >= (1LL << 31) - 1 || nnz >= (1LL << 31) - 2 * SLA_SPMV_TILE)
     return sla_fail(c, SLA_ERR_INVALID, "csr: dimensions or nnz exceed the int32 index range of this build");
   sla_csr* A = new (std::nothrow) sla_csr();

@@ -134,6 +134,7 @@ extern "C" sla_status sla_bicgstab_init(sla_ctx* c, const sla_csr* A, const sla_
 }
 
 extern "C" sla_status sla_bicgstab_step(sla_ctx* c, const sla_csr* A, const sla_vec* r0hat, sla_krylov* st) {
+  SLA_GUARD(c);
   if (!c || !A || !r0hat || !st || st->kind != SLA_BICGSTAB_) return SLA_ERR_INVALID;
   if (A->m != st->n || csr_xdim(A) != st->n || r0hat->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "bicgstabStep: dimensions differ");
   const int64_t n = st->n;
@@ -170,6 +171,7 @@ extern "C" sla_status sla_cgs_init(sla_ctx* c, const sla_csr* A, const sla_vec* 
 }
 
 extern "C" sla_status sla_cgs_step(sla_ctx* c, const sla_csr* A, const sla_vec* rhat, sla_krylov* st) {
+  SLA_GUARD(c);
   if (!c || !A || !rhat || !st || st->kind != SLA_CGS_) return SLA_ERR_INVALID;
   if (A->m != st->n || csr_xdim(A) != st->n || rhat->n != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgsStep: dimensions differ");
   const int64_t n = st->n;
@@ -218,6 +220,7 @@ extern "C" sla_status sla_cgne_init(sla_ctx* c, const sla_csr* A, const sla_vec*
 }
 
 extern "C" sla_status sla_cgne_step(sla_ctx* c, const sla_csr* A, sla_krylov* st) {
+  SLA_GUARD(c);
   if (!c || !A || !st || st->kind != SLA_CGNE_) return SLA_ERR_INVALID;
   if (A->dist && !A->T) return sla_fail(c, SLA_ERR_INVALID, "cgneStep: attach the distributed transpose of the row-partitioned matrix first");
   if (A->m != st->n || csr_xdim(A) != st->n) return sla_fail(c, SLA_ERR_SIZE_MISMATCH, "cgneStep: dimensions differ");
@@ -625,6 +628,7 @@ static sla_status dense_alloc(sla_ctx* c, int64_t rows, int64_t cols, sla_dense*
 // projection once (CGS2) — used by GMRES only, because single-pass CGS loses orthogonality on clustered spectra.
 template <bool GM>
 static sla_status arnoldi_step(sla_ctx* c, const sla_csr* A, sla_dense* Q, int j, double* w, bool reorth, const arn_dev& d, double tol, double g0) {
+  SLA_GUARD(c);
   const int64_t n = Q->rows, ld = Q->ld;
   SLA_TRY(sla_spmv_launch(c, A, Q->d + (int64_t)j * ld, w, EPI_NONE, nullptr, nullptr, FIN_STORE, S_TMP0));
   const int nq = j + 1;

@@ -358,10 +358,12 @@ class SpMatrix:
     # -- construction (SpMatrix.hs:128-135, 184-191, 205-241)
     @staticmethod
     def fromCOO(dims, i, j, v, ctx=None):
-        ctx = ctx or default_context()
         ia, ip = _i64(i)
         ja, jp = _i64(j)
         va, vp = _f64(v)
+        if not (ia.size == ja.size == va.size):          # the C side would read past the shorter buffer
+            raise ValueError(f"fromCOO: i, j and v must have the same length ({ia.size}, {ja.size}, {va.size})")
+        ctx = ctx or default_context()
         h = C.c_void_p()
         ctx.check(ctx.lib.sla_csr_from_coo(ctx.h, dims[0], dims[1], ia.size, ip, jp, vp, C.byref(h)))
         return SpMatrix(ctx, h)
@@ -380,10 +382,12 @@ class SpMatrix:
 
     @staticmethod
     def fromCSR(m, n, row_ptr, col_idx, val, ctx=None):
-        ctx = ctx or default_context()
         rp = np.ascontiguousarray(row_ptr, dtype=np.int32)
         ci = np.ascontiguousarray(col_idx, dtype=np.int32)
         va, vp = _f64(val)
+        if rp.size != m + 1 or ci.size != va.size:
+            raise ValueError(f"fromCSR: row_ptr needs m + 1 = {m + 1} entries (got {rp.size}) and col_idx / val equal lengths ({ci.size}, {va.size})")
+        ctx = ctx or default_context()
         h = C.c_void_p()
         ctx.check(ctx.lib.sla_csr_from_csr(ctx.h, m, n, ci.size, rp.ctypes.data_as(C.POINTER(C.c_int32)),
                                            ci.ctypes.data_as(C.POINTER(C.c_int32)), vp, C.byref(h)))
@@ -403,6 +407,8 @@ class SpMatrix:
 
     @staticmethod
     def mkDiagonal(n, xx, ctx=None):
+        if len(xx) < n:
+            raise ValueError(f"mkDiagonal: {n} diagonal entries expected, got {len(xx)}")
         return SpMatrix.fromCOO((n, n), np.arange(n), np.arange(n), np.asarray(xx, dtype=np.float64)[:n], ctx)
 
     @staticmethod

@@ -122,3 +122,20 @@ def test_cpp_mirror_runs_reference_specs_on_gpu(lib, tmp_path):
     p = subprocess.run([_build_cpp_mirror(tmp_path)], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert "mirror_smoke ok" in p.stdout
+
+
+def test_python_wrappers_check_buffer_lengths():
+    """the wrappers pass raw pointers, so inconsistent lengths must be refused before the library reads past a buffer
+    (checked before any context is needed: runs without a GPU)."""
+    import pytest
+
+    import sparse_linear_algebra_b200 as sla
+
+    with pytest.raises(ValueError):
+        sla.SpMatrix.fromCOO((3, 3), [0, 1], [0, 1, 2], [1.0, 2.0])
+    with pytest.raises(ValueError):
+        sla.SpMatrix.fromCSR(3, 3, [0, 1, 2], [0, 1], [1.0, 2.0])            # row_ptr too short
+    with pytest.raises(ValueError):
+        sla.SpMatrix.fromCSR(2, 3, [0, 1, 2], [0, 1], [1.0])                 # col / val differ
+    with pytest.raises(ValueError):
+        sla.SpMatrix.mkDiagonal(4, [1.0, 2.0])
