@@ -243,7 +243,7 @@ def parity_cfg2(A, y, starts, rank, world, dist, n, k):
     nloc = starts[rank + 1] - starts[rank]
     xh_full = np.asarray(ora.SpVector.synth(SEED_CFG2 + 1, n).toDenseListSV())
     p2p_mode = getattr(A, "dist_p2p_mode", 0)
-    mine = parity_rows(y.toDenseListSV(), starts[rank], nloc, n, k, SEED_CFG2, ora.GEN_UNIFORM, 0, xh_full, exact=(p2p_mode != 2))
+    mine = parity_rows(y.toDenseListSV(), starts[rank], nloc, n, k, SEED_CFG2, ora.GEN_UNIFORM, 0, xh_full, exact=(p2p_mode not in (2, 5)))
     del xh_full
     if dist is not None:
         allp = [None] * world
@@ -253,7 +253,7 @@ def parity_cfg2(A, y, starts, rank, world, dist, n, k):
     return {"what": "rows of y = A x (cfg 2, this run) vs oracle.synth_row folded left to right",
             "rows": sum(q["rows"] for q in allp), "bit_exact_rows": sum(q["bit_exact_rows"] for q in allp),
             "max_err_over_bound": max(q["max_err_over_bound"] for q in allp),
-            "criterion": "bit-exact" if p2p_mode != 2 else "(k+2) u sum|a_ij x_j| (arrival-order exchange folds each row in rotated column order)",
+            "criterion": "bit-exact" if p2p_mode not in (2, 5) else "(k+2) u sum|a_ij x_j| (arrival-order / two-phase exchange folds each row in rotated column order)",
             "ok": all(q["bad_rows"] == 0 for q in allp)}
 
 
@@ -385,7 +385,8 @@ def run_gpu(args):
                                 "x_exchange": {1: "peer-memory push kernel (csrc/p2p.cu)",
                                                2: "copy-engine all-gather consumed in arrival order (csrc/p2p.cu mode 2)",
                                                3: "LL halo kernel (csrc/p2p.cu mode 3)",
-                                               4: "copy-engine all-gather waited for as a whole (csrc/p2p.cu mode 4)"}.get(
+                                               4: "copy-engine all-gather waited for as a whole (csrc/p2p.cu mode 4)",
+                                               5: "two-phase peer-memory push under rotated near/far panels (csrc/p2p.cu mode 5)"}.get(
                                     getattr(A, "dist_p2p_mode", 0), "ncclAllGather" if getattr(A, "dist_allgather", False) else "nccl send/recv")}
 
     def sptrsv_extra(tag, M, rhs):

@@ -15,6 +15,8 @@ for variant in ${CHECKS:-auto x0 nccl}; do
     x0)   ENVS="SLA_P2P_X=0";;
     x1)   ENVS="SLA_P2P_X=1";;
     x4)   ENVS="SLA_P2P_X=4";;
+    x5)   ENVS="SLA_P2P_X=5 SLA_P2P_ARRIVAL_ALWAYS=1";;      # ALWAYS: the small check matrices take the phased path too
+    x5p*c*) v=${variant#x5p}; ENVS="SLA_P2P_X=5 SLA_P2P_PANELS=${v%%c*} SLA_P2P_PUSH_CTAS=${v##*c}";;   # e.g. x5p1,1,2c64
     arrival) ENVS="SLA_P2P_X=2 SLA_P2P_ARRIVAL_ALWAYS=1";;
     noinline) ENVS="SLA_P2P_INLINE=0";;
     nccl) ENVS="SLA_P2P=0";;
@@ -28,6 +30,8 @@ for variant in ${BENCHES:-auto x0}; do
     auto) ENVS="";;
     x0)   ENVS="SLA_P2P_X=0";;
     x4)   ENVS="SLA_P2P_X=4";;
+    x5)   ENVS="SLA_P2P_X=5";;
+    x5p*c*) v=${variant#x5p}; ENVS="SLA_P2P_X=5 SLA_P2P_PANELS=${v%%c*} SLA_P2P_PUSH_CTAS=${v##*c}";;   # e.g. x5p1,1,2c64
     arrival) ENVS="SLA_P2P_X=2 SLA_P2P_ARRIVAL_ALWAYS=1";;
     nccl) ENVS="SLA_P2P=0";;
   esac

@@ -437,10 +437,17 @@ void sla_p2p_free(sla_ctx* c);
 void* sla_p2p_window(sla_ctx* c);                                                                 // multi.cu: one process, several GPUs
 sla_status sla_p2p_attach_direct(sla_ctx* c, void* const* wins);
 bool sla_xwin_active(const sla_csr* A);
-int sla_xwin_mode(const sla_csr* A);                                                             // 0 off, 1 push kernel, 2 arrival order, 3 LL halo, 4 copy-engine all-gather
+int sla_xwin_mode(const sla_csr* A);                                                             // 0 off, 1 push kernel, 2 arrival order, 3 LL halo, 4 copy-engine all-gather, 5 two-phase push
 sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_local);
 sla_status sla_p2p_arrival_wait(sla_ctx* c, const sla_csr* A, int src);
 sla_status sla_p2p_arrival_end(sla_ctx* c);
+sla_status sla_p2p_twophase_begin(sla_ctx* c, const sla_csr* A, const double* x_local);          // mode 5
+sla_status sla_p2p_twophase_wait(sla_ctx* c, const sla_csr* A, int phase);
+// Rotated column panels of a row-partitioned matrix with equal blocks (spmv.cu): column j belongs to the block of predecessor
+// k = ((own_end - 1 - j) mod n) / m of this rank (k = 0: own block); panel p holds the predecessors kb[p] <= k < kb[p + 1].
+#define SLA_ROT_MAX 8
+struct sla_rot_spec { long long n, own_end, m; int P; int kb[SLA_ROT_MAX + 1]; };
+sla_status sla_csr_force_rot_panels(sla_ctx* c, sla_csr* A, const sla_rot_spec* spec);
 sla_status sla_p2p_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local);
 void sla_xwin_free(sla_csr* A);
 void sla_csr_free_bsr(sla_csr* A);

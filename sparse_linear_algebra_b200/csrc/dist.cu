@@ -91,7 +91,12 @@ sla_status sla_dist_attach(sla_ctx* c, const void* nccl_id128) {
     ncclComm_t cx = nullptr;
     if (g_nccl.CommSplit(comm, 0, c->rank, &cx, nullptr) == ncclSuccess && cx) c->nccl_x = (void*)cx;
   }
-  SLA_CUDA(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  {
+    // the exchange stream outranks the compute stream: its (few) CTAs are scheduled ahead of the panel kernels they run under
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    SLA_CUDA(c, cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+  }
   SLA_CUDA(c, cudaEventCreateWithFlags(&c->ev_x0, cudaEventDisableTiming));
   for (int p = 0; p < SLA_MAX_PANELS; ++p) SLA_CUDA(c, cudaEventCreateWithFlags(&c->ev_panel[p], cudaEventDisableTiming));
   return SLA_OK;

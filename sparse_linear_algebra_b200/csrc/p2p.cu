@@ -30,6 +30,7 @@
 
 #include <new>
 #include <stdlib.h>
+#include <vector>
 
 #define P2P_AR_THREADS 128
 #define P2P_AR_WINDOW_BYTES (P2P_FLAG_BYTES + 2 * SLA_MAX_WORLD * P2P_MAX_NV * 8)   // [2][W] u64 flags | [2][W][P2P_MAX_NV] doubles
@@ -60,6 +61,8 @@ struct sla_xwin {                                // per distributed matrix: [256
   p2p_item* d_items;
   int nitems;                                    // send items; LL windows: followed by nrecv unpack items
   int nrecv;
+  // mode 5 (two-phase push): the send items re-ordered by phase, the peers / sources of each phase
+  p2p_item* d_items2; int nphase, n_phase[SLA_ROT_MAX]; unsigned dst_mask[SLA_ROT_MAX], src_mask[SLA_ROT_MAX]; unsigned int* d_ticket2; int push_ctas, bulk;
   unsigned int* d_ticket;
   unsigned long long seq;
 };
@@ -81,15 +84,28 @@ p2p_allreduce_kernel(sla_p2p_args a, int nv, int src, int fin, int dst, double* 
 __global__ void __launch_bounds__(P2P_PUSH_THREADS)
 p2p_push_kernel(const p2p_item* __restrict__ items, int nitems, char* const* __restrict__ peer, size_t buf_off,
                 const double* __restrict__ x_local, int rank, int world, unsigned long long seq, unsigned int* ticket, int* err) {
-  if ((int)blockIdx.x < nitems) {
-    const p2p_item it = items[blockIdx.x];
+  // one CTA per item (the launch sizes the grid that way; the loop is the same code as the persistent two-phase kernel below)
+  for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+    const p2p_item it = items[w];
     double* dst = reinterpret_cast<double*>(peer[it.peer] + buf_off) + it.goff;
     const double* src = x_local + it.src;
     if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0) {
       const int n2 = it.len >> 1;
       const double2* s2 = reinterpret_cast<const double2*>(src);
       double2* d2 = reinterpret_cast<double2*>(dst);
-      for (int i = threadIdx.x; i < n2; i += P2P_PUSH_THREADS) d2[i] = s2[i];
+      for (int base = 0; base < n2; base += P2P_PUSH_THREADS * 8) {
+        double2 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * P2P_PUSH_THREADS + (int)threadIdx.x;
+          if (i < n2) r[u] = s2[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * P2P_PUSH_THREADS + (int)threadIdx.x;
+          if (i < n2) d2[i] = r[u];
+        }
+      }
       if ((it.len & 1) && threadIdx.x == 0) dst[it.len - 1] = src[it.len - 1];
     } else {
       for (int i = threadIdx.x; i < it.len; i += P2P_PUSH_THREADS) dst[i] = src[i];
@@ -149,6 +165,114 @@ p2p_halo_ll_kernel(const p2p_item* __restrict__ items, int nsend, int nrecv, cha
     }
     dst[i] = __hiloint2double((int)v.z, (int)v.x);
   }
+}
+
+// mode 5: one PHASE of the two-phase exchange — the planned pieces for the peers of this phase, then (last CTA) this rank's
+// flag on exactly those peers.  Nobody waits here: the consumer's wait kernel precedes the panel kernel that needs the data.
+__global__ void __launch_bounds__(P2P_PUSH_THREADS)
+p2p_push_phase_kernel(const p2p_item* __restrict__ items, int nitems, char* const* __restrict__ peer, size_t buf_off,
+                      const double* __restrict__ x_local, int rank, int world, unsigned dst_mask, unsigned long long seq, unsigned int* ticket) {
+  // persistent: a FEW CTAs walk the items, so that the (#>) panel kernel launched behind this one finds room on every SM
+  for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+    const p2p_item it = items[w];
+    double* dst = reinterpret_cast<double*>(peer[it.peer] + buf_off) + it.goff;
+    const double* src = x_local + it.src;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0) {
+      const int n2 = it.len >> 1;
+      const double2* s2 = reinterpret_cast<const double2*>(src);
+      double2* d2 = reinterpret_cast<double2*>(dst);
+      for (int base = 0; base < n2; base += P2P_PUSH_THREADS * 8) {
+        double2 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * P2P_PUSH_THREADS + (int)threadIdx.x;
+          if (i < n2) r[u] = s2[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * P2P_PUSH_THREADS + (int)threadIdx.x;
+          if (i < n2) d2[i] = r[u];
+        }
+      }
+      if ((it.len & 1) && threadIdx.x == 0) dst[it.len - 1] = src[it.len - 1];
+    } else {
+      for (int i = threadIdx.x; i < it.len; i += P2P_PUSH_THREADS) dst[i] = src[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) *ticket = 0u;
+  __threadfence_system();
+  const int t = threadIdx.x;
+  if (t < world && ((dst_mask >> t) & 1u)) st_release_sys_u64(reinterpret_cast<unsigned long long*>(peer[t]) + rank, seq);
+}
+
+// mode 5, the same phase driven by the TMA unit: ONE thread per CTA moves 16 KB pieces global -> shared -> peer global with bulk
+// copies (cp.async.bulk, SASS UBLKCP) through a ring of P2P_BULK_STAGES buffers — two loads and two stores in flight per CTA, no
+// LSU instructions and no registers taken from the (#>) kernel that shares the SM.  Every piece is 16-byte aligned (checked when
+// the mode is enabled).
+#define P2P_BULK_STAGES 4
+#define P2P_BULK_BYTES 16384
+#define P2P_BULK_LEN (P2P_BULK_BYTES / 8)
+__device__ __forceinline__ uint32_t p2p_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(32)
+p2p_push_bulk_kernel(const p2p_item* __restrict__ items, int nitems, char* const* __restrict__ peer, size_t buf_off,
+                     const double* __restrict__ x_local, int rank, int world, unsigned dst_mask, unsigned long long seq, unsigned int* ticket) {
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(8) uint64_t bar[P2P_BULK_STAGES];
+  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P2P_BULK_STAGES; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(p2p_smem_u32(&bar[i])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int nj = b < nitems ? (nitems - b + G - 1) / G : 0;
+    constexpr int L = P2P_BULK_STAGES - 2;                    // loads ahead of the store being issued
+    auto load = [&](int j) {
+      const p2p_item it = items[b + j * G];
+      const int st = j % P2P_BULK_STAGES;
+      const uint32_t bytes = (uint32_t)it.len * 8u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p2p_smem_u32(&bar[st])), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(p2p_smem_u32(ring + (size_t)st * P2P_BULK_BYTES)), "l"(x_local + it.src), "r"(bytes), "r"(p2p_smem_u32(&bar[st])) : "memory");
+    };
+    for (int j = 0; j < L && j < nj; ++j) load(j);
+    for (int j = 0; j < nj; ++j) {
+      if (j + L < nj) {
+        // the buffer of piece j + L was last read by the store of piece j - 2: at most ONE store (j - 1) may still be reading
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        load(j + L);
+      }
+      const int st = j % P2P_BULK_STAGES;
+      const uint32_t parity = (uint32_t)(j / P2P_BULK_STAGES) & 1u;
+      asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                   ::"r"(p2p_smem_u32(&bar[st])), "r"(parity) : "memory");
+      const p2p_item it = items[b + j * G];
+      double* dst = reinterpret_cast<double*>(peer[it.peer] + buf_off) + it.goff;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(dst), "r"(p2p_smem_u32(ring + (size_t)st * P2P_BULK_BYTES)), "r"((uint32_t)it.len * 8u) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every store of this CTA has been performed
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence_system();
+  }
+  __syncwarp();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncwarp();
+  if (!last) return;
+  if (threadIdx.x == 0) *ticket = 0u;
+  __threadfence_system();
+  const int t = threadIdx.x;
+  if (t < world && ((dst_mask >> t) & 1u)) st_release_sys_u64(reinterpret_cast<unsigned long long*>(peer[t]) + rank, seq);
 }
 
 // mode 2: the flag that follows a copy-engine block on the comm stream, and the per-source wait before a panel kernel
@@ -423,6 +547,83 @@ extern "C" sla_status sla_csr_p2p_enable(sla_ctx* c, sla_csr* A, int on) {
     }
   }
   const bool was_in_window = d->xwin->enabled && !d->xwin->ll;
+  if (!on && d->xwin->enabled && d->xwin->mode == 5) sla_csr_free_panels(A);        // the rotated panels belong to the two-phase exchange
+  if (on == 5 && d->dense_equal && c->comm_stream != nullptr && !d->xwin->ll) {
+    // Phased push (dense equal-block plans): the (#>) runs ROTATED column panels — the own block first, then the blocks of the
+    // predecessors in growing groups — and the blocks of group p travel (TMA bulk copies issued by a few one-thread CTAs on a
+    // high-priority side stream) under the kernels of the panels before it.  Balanced: in each phase every rank sends and
+    // receives the same amount.  Rows are folded panel by panel: within the fp64 bound of SURVEY.md 8(d), like arrival order.
+    const int W = c->world;
+    sla_xwin* X = d->xwin;
+    const bool eligible = W >= 2 && W <= 31 && A->n % W == 0 && A->m == A->n / W && d->row0 == (int64_t)c->rank * A->m && A->m % 16 == 0 && A->m > 0;
+    const bool big_x = (uint64_t)A->n * 8u > (56u << 20);   // like mode 2: panels pay only when x would not stay L2-resident anyway
+    mode = 1;
+    if (eligible && (big_x || getenv("SLA_P2P_ARRIVAL_ALWAYS"))) {
+      X->push_ctas = 64;                                    // measured at 4 ranks, cfg 2: 32 -> 0.491, 64 -> 0.482, 128 -> 0.502 ms per (#>)
+      if (const char* e = getenv("SLA_P2P_PUSH_CTAS")) X->push_ctas = atoi(e) > 0 ? atoi(e) : 64;
+      // Panel p = the blocks of predecessors kb[p] .. kb[p + 1] - 1 (panel 0 = own block, nothing to wait for); phase p brings
+      // exactly those blocks.  Default: 1, 1, 2, 4, ... blocks — every phase is at most as large as everything computed before
+      // it, and a block of columns takes longer to multiply than to receive (cfg 2: ~2x).  SLA_P2P_PANELS="1,1,2" overrides.
+      sla_rot_spec rs;
+      rs.n = A->n; rs.m = A->m; rs.own_end = d->row0 + A->m; rs.P = 0; rs.kb[0] = 0;
+      {
+        int sizes[SLA_ROT_MAX], ns = 0;
+        const char* e = getenv("SLA_P2P_PANELS");
+        while (e && *e && ns < SLA_ROT_MAX) {
+          const int v = atoi(e);
+          if (v <= 0) { ns = 0; break; }
+          sizes[ns++] = v;
+          e = strchr(e, ',');
+          if (e) ++e;
+        }
+        int tot = 0;
+        for (int i = 0; i < ns; ++i) tot += sizes[i];
+        if (ns < 2 || tot != W || sizes[0] != 1) {            // default: 1, 1, 2, 4, ...
+          ns = 0; sizes[ns++] = 1;
+          int left = W - 1, next = 1;
+          while (left > 0) {
+            const int take = (next < left && ns < SLA_ROT_MAX - 1) ? next : left;
+            sizes[ns++] = take; left -= take;
+            next = ns == 2 ? 2 : next * 2;
+          }
+        }
+        rs.P = ns;
+        for (int i = 0; i < ns; ++i) rs.kb[i + 1] = rs.kb[i] + sizes[i];
+      }
+      X->nphase = rs.P;
+      for (int ph = 0; ph < SLA_ROT_MAX; ++ph) X->dst_mask[ph] = X->src_mask[ph] = 0u;
+      for (int ph = 1; ph < rs.P; ++ph)
+        for (int k = rs.kb[ph]; k < rs.kb[ph + 1]; ++k) {
+          X->dst_mask[ph] |= 1u << ((c->rank + k) % W);        // I am predecessor k of rank r + k
+          X->src_mask[ph] |= 1u << ((c->rank - k + W) % W);
+        }
+      // items re-ordered by phase
+      std::vector<p2p_item> all((size_t)(X->nitems > 0 ? X->nitems : 1)), ord;
+      if (X->nitems > 0) SLA_CUDA(c, cudaMemcpy(all.data(), X->d_items, sizeof(p2p_item) * (size_t)X->nitems, cudaMemcpyDeviceToHost));
+      bool aligned = true;
+      for (int ph = 0; ph < rs.P; ++ph) {
+        X->n_phase[ph] = 0;
+        for (int i = 0; i < X->nitems; ++i) {
+          if (!((X->dst_mask[ph] >> all[i].peer) & 1u)) continue;
+          for (int o = 0; o < all[i].len; o += P2P_BULK_LEN) {      // pieces of one ring buffer
+            p2p_item h = all[i];
+            h.len = all[i].len - o < P2P_BULK_LEN ? all[i].len - o : P2P_BULK_LEN;
+            h.goff += o; h.src += o;
+            aligned = aligned && (h.len % 2 == 0) && (h.goff % 2 == 0) && (h.src % 2 == 0);
+            ord.push_back(h); X->n_phase[ph]++;
+          }
+        }
+      }
+      X->bulk = aligned && !getenv("SLA_P2P_PUSH_LSU");
+      if (X->bulk)
+        SLA_CUDA(c, cudaFuncSetAttribute(p2p_push_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2P_BULK_STAGES * P2P_BULK_BYTES));
+      if (!X->d_items2) SLA_CUDA(c, cudaMalloc(&X->d_items2, sizeof(p2p_item) * (size_t)(ord.size() > 0 ? ord.size() : 1)));
+      if (!ord.empty()) SLA_CUDA(c, cudaMemcpy(X->d_items2, ord.data(), sizeof(p2p_item) * ord.size(), cudaMemcpyHostToDevice));
+      if (!X->d_ticket2) { SLA_CUDA(c, cudaMalloc(&X->d_ticket2, sizeof(unsigned int) * SLA_ROT_MAX)); SLA_CUDA(c, cudaMemset(X->d_ticket2, 0, sizeof(unsigned int) * SLA_ROT_MAX)); }
+      SLA_TRY(sla_csr_force_rot_panels(c, A, &rs));
+      if (A->npanels == rs.P) mode = 5;
+    }
+  }
   d->xwin->enabled = on ? 1 : 0;
   d->xwin->mode = mode;
   SLA_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -467,6 +668,43 @@ sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_l
   return SLA_OK;
 }
 
+// mode 5, step 1: both phases of the push on the comm stream (phase A first); flips the double buffer
+sla_status sla_p2p_twophase_begin(sla_ctx* c, const sla_csr* A, const double* x_local) {
+  sla_dist_info* d = A->dist;
+  sla_xwin* X = d->xwin;
+  X->seq++;
+  const size_t off = P2P_FLAG_BYTES + (size_t)(X->seq & 1ull) * X->buf_bytes;
+  SLA_CUDA(c, cudaEventRecord(c->ev_x0, c->stream));                   // x is final; my earlier panel kernels are done
+  SLA_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_x0, 0));
+  int first = 0;
+  for (int ph = 0; ph < X->nphase; ++ph) {
+    if (X->dst_mask[ph]) {
+      int grid = X->n_phase[ph] > 0 ? X->n_phase[ph] : 1;
+      if (grid > X->push_ctas) grid = X->push_ctas;
+      if (X->bulk)
+        p2p_push_bulk_kernel<<<grid, 32, P2P_BULK_STAGES * P2P_BULK_BYTES, c->comm_stream>>>(X->d_items2 + first, X->n_phase[ph], X->d_peer, off, x_local,
+                                                                                          c->rank, c->world, X->dst_mask[ph], X->seq, X->d_ticket2 + ph);
+      else
+        p2p_push_phase_kernel<<<grid, P2P_PUSH_THREADS, 0, c->comm_stream>>>(X->d_items2 + first, X->n_phase[ph], X->d_peer, off, x_local, c->rank, c->world,
+                                                                            X->dst_mask[ph], X->seq, X->d_ticket2 + ph);
+      SLA_LAUNCH_CHECK(c);
+    }
+    first += X->n_phase[ph];
+  }
+  SLA_CUDA(c, cudaEventRecord(c->ev_panel[0], c->comm_stream));       // "my pushes have read x_local"
+  d->xfull = reinterpret_cast<double*>(X->win + off);
+  return SLA_OK;
+}
+
+// mode 5, step 2 (compute stream): the blocks of phase ph have arrived
+sla_status sla_p2p_twophase_wait(sla_ctx* c, const sla_csr* A, int ph) {
+  sla_xwin* X = A->dist->xwin;
+  if (!X->src_mask[ph]) return SLA_OK;
+  p2p_wait_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const unsigned long long*>(X->win), X->src_mask[ph], X->seq, c->p2p->d_err);
+  SLA_LAUNCH_CHECK(c);
+  return SLA_OK;
+}
+
 // mode 2, last step (compute stream): whatever follows the (#>) may overwrite x_local, so it must wait until the copy
 // engines have finished reading it (the panel kernels only wait for INCOMING blocks)
 sla_status sla_p2p_arrival_end(sla_ctx* c) {
@@ -498,6 +736,11 @@ sla_status sla_p2p_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_loca
     }
     return SLA_OK;
   }
+  if (X->mode == 5) {
+    SLA_TRY(sla_p2p_twophase_begin(c, A, x_local));
+    for (int ph = 0; ph < X->nphase; ++ph) SLA_TRY(sla_p2p_twophase_wait(c, A, ph));
+    return sla_p2p_arrival_end(c);
+  }
   if (X->mode == 2 || X->mode == 4) {           // (#>) drives these itself; other callers get the whole gather
     SLA_TRY(sla_p2p_arrival_begin(c, A, x_local));
     SLA_TRY(sla_p2p_arrival_wait(c, A, -1));
@@ -521,7 +764,7 @@ void sla_xwin_free(sla_csr* A) {
   if (c) cudaStreamSynchronize(c->stream);
   if (c && c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c) close_peers(c, X->peer);
-  cudaFree(X->d_peer); cudaFree(X->d_items); cudaFree(X->d_ticket);
+  cudaFree(X->d_peer); cudaFree(X->d_items); cudaFree(X->d_ticket); cudaFree(X->d_items2); cudaFree(X->d_ticket2);
   if (d->xfull && (char*)d->xfull >= X->win && (char*)d->xfull < X->win + P2P_FLAG_BYTES + 2 * X->buf_bytes) d->xfull = nullptr;   // it pointed into the window
   if (c && c->n_parked < SLA_MAX_PARKED) c->parked[c->n_parked++] = X->win;   // else: leaked until process exit
   delete X;

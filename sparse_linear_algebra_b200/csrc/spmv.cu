@@ -516,6 +516,40 @@ __global__ void panel_fill_kernel(const int* __restrict__ row_ptr, const int* __
   }
 }
 
+// ROTATED panels (p2p.cu mode 5): panel p = the column blocks of this rank's predecessors kb[p] .. kb[p + 1] - 1 (0 = own block).
+// Inside a panel a row keeps its entries in ascending column order.
+__device__ __forceinline__ int rot_panel_of(int c, const sla_rot_spec& rs) {
+  long long d = rs.own_end - 1 - (long long)c;
+  if (d < 0) d += rs.n;
+  const int k = (int)(d / rs.m);
+  int p = 0;
+  while (p + 1 < rs.P && k >= rs.kb[p + 1]) ++p;
+  return p;
+}
+__global__ void rot_count_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, int m, const sla_rot_spec rs, int* __restrict__ len) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  for (int p = 0; p < rs.P; ++p) len[(size_t)p * m + r] = 0;
+  for (int q = row_ptr[r]; q < row_ptr[r + 1]; ++q) len[(size_t)rot_panel_of(col[q], rs) * m + r] += 1;
+}
+__global__ void rot_fill_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ val, int m,
+                                const sla_rot_spec rs, const sla_panel* __restrict__ panels) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  int cur[SLA_ROT_MAX];
+#pragma unroll
+  for (int p = 0; p < SLA_ROT_MAX; ++p) cur[p] = p < rs.P ? panels[p].row_ptr[r] : 0;
+  for (int q = row_ptr[r]; q < row_ptr[r + 1]; ++q) {
+    const int cidx = col[q];
+    const int p = rot_panel_of(cidx, rs);
+    int at = 0;
+#pragma unroll
+    for (int t = 0; t < SLA_ROT_MAX; ++t) if (t == p) { at = cur[t]; cur[t] = at + 1; }
+    panels[p].col[at] = cidx;
+    panels[p].val[at] = val[q];
+  }
+}
+
 __global__ void set_last_kernel(int32_t* row_ptr, const int32_t* len, int m) {
   if (threadIdx.x == 0 && blockIdx.x == 0) row_ptr[m] = m > 0 ? row_ptr[m - 1] + len[m - 1] : 0;
 }
@@ -550,11 +584,14 @@ void sla_csr_free_panels(sla_csr* A) {
   A->panels = nullptr; A->npanels = 0; A->chunk_ready = 0;
 }
 
-static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
+// rs != nullptr: rotated panels (blocks of predecessors) instead of P equal column ranges
+static sla_status build_panels(sla_ctx* c, sla_csr* A, int P, const sla_rot_spec* rs = nullptr) {
   const int m = (int)A->m;
+  const bool rot = rs != nullptr;
   int width = (int)((A->n + P - 1) / P);
   width = (width + 15) & ~15;
-  P = (int)((A->n + width - 1) / width);
+  P = rot ? rs->P : (int)((A->n + width - 1) / width);
+  if (rot) width = -1;                 // no uniform width: sla_csr_force_panels never mistakes these for its own
   if (P < 2) return SLA_OK;
   int *start = nullptr, *len = nullptr;
   sla_panel* d_panels = nullptr;
@@ -567,7 +604,8 @@ static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
   do {
     if (cudaMalloc(&start, sizeof(int) * (size_t)P * m) != cudaSuccess || cudaMalloc(&len, sizeof(int) * (size_t)P * m) != cudaSuccess ||
         cudaMalloc(&d_panels, sizeof(sla_panel) * P) != cudaSuccess) { s = sla_fail(c, SLA_ERR_ALLOC, "spmv plan: cudaMalloc failed"); break; }
-    panel_split_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(A->row_ptr, A->col, m, P, width, start, len);
+    if (rot) rot_count_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(A->row_ptr, A->col, m, *rs, len);
+    else panel_split_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(A->row_ptr, A->col, m, P, width, start, len);
     c->launches++;
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, len, len, m, c->stream);
@@ -594,7 +632,10 @@ static sla_status build_panels(sla_ctx* c, sla_csr* A, int P) {
     }
     if (s != SLA_OK) break;
     cudaMemcpyAsync(d_panels, A->panels, sizeof(sla_panel) * P, cudaMemcpyHostToDevice, c->stream);
-    if (A->nnz > 0) {
+    if (A->nnz > 0 && rot) {
+      rot_fill_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(A->row_ptr, A->col, A->val, m, *rs, d_panels);
+      c->launches++;
+    } else if (A->nnz > 0) {
       int64_t blocks = (A->nnz + 255) / 256;
       if (blocks > SLA_NUM_SMS * 32) blocks = SLA_NUM_SMS * 32;
       panel_fill_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(A->row_ptr, A->col, A->val, m, A->nnz, width, start, d_panels);
@@ -663,6 +704,13 @@ sla_status sla_csr_force_panels(sla_ctx* c, sla_csr* A, int P) {
   sla_csr_free_panels(A);
   if (P < 2) return SLA_OK;
   return build_panels(c, A, P);
+}
+
+// p2p.cu mode 5: rotated panels of a row-partitioned matrix (collective: every rank calls it with its own rotation)
+sla_status sla_csr_force_rot_panels(sla_ctx* c, sla_csr* A, const sla_rot_spec* spec) {
+  sla_csr_free_panels(A);
+  if (!spec || spec->P < 2 || spec->P > SLA_ROT_MAX || spec->m <= 0) return SLA_OK;
+  return build_panels(c, A, spec->P, spec);
 }
 
 // Sums the two per-CTA partial arrays of an SpMV epilogue in a fixed order and post-processes the Krylov scalars
@@ -794,6 +842,33 @@ static sla_status spmv_launch_arrival(sla_ctx* c, const sla_csr* A, const double
   return skip ? SLA_OK : sla_p2p_arrival_end(c);
 }
 
+// Row-partitioned (#>) with the PHASED push (p2p.cu mode 5): panel 0 (own block) runs at once, panel p after phase p has arrived —
+// which travelled under the kernels of the panels before it.
+static sla_status spmv_launch_twophase(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi, const double* u0, int fin, int dst) {
+  const bool skip = c->skip_exchange != 0;                // diagnostic: kernels only
+  if (!skip) SLA_TRY(sla_p2p_twophase_begin(c, A, x));
+  SpmvArgs a;
+  a.hints = A->hints; a.x = x; a.u0 = u0; a.fin = fin; a.dst = dst;
+  dist_args(A, &a.dx); a.tile0 = 0;
+  double* ybuf = y;
+  if (epi == EPI_RESNORM) {
+    if (!c->scratch_r || c->scratch_r->n != A->m) {
+      sla_vec_free(c->scratch_r); c->scratch_r = nullptr;
+      SLA_TRY(sla_vec_alloc(c, A->m, &c->scratch_r));
+    }
+    ybuf = c->scratch_r->d;
+  }
+  for (int ph = 0; ph < A->npanels; ++ph) {
+    if (!skip) SLA_TRY(sla_p2p_twophase_wait(c, A, ph));
+    const sla_panel& pn = A->panels[ph];
+    a.row_ptr = pn.row_ptr; a.col = pn.col; a.val = pn.val; a.tile_row = pn.tile_row;
+    a.ntiles = pn.ntiles; a.skew_a = pn.skew_a;
+    a.yin = ph == 0 ? nullptr : ybuf; a.y = ybuf;
+    SLA_TRY(launch_any(c, ph == A->npanels - 1 ? epi : EPI_NONE, ph > 0, 1, a));
+  }
+  return skip ? SLA_OK : sla_p2p_arrival_end(c);
+}
+
 // y = A x with an optional fused epilogue.  u1 is reserved (EPI_DOT2_YY uses y itself).
 // For a row block of a distributed matrix, x is the LOCAL slice; the remote entries are exchanged first.
 sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi,
@@ -804,6 +879,8 @@ sla_status sla_spmv_launch(sla_ctx* c, const sla_csr* A, const double* x, double
   if (A->band && !dist) return band_launch(c, A, x, y, epi, u0, fin, dst);
   if (dist && c->world > 1 && sla_xwin_mode(A) == 2 && A->npanels == c->world && A->m > 0)
     return spmv_launch_arrival(c, A, x, y, epi, u0, fin, dst);
+  if (dist && c->world > 1 && sla_xwin_mode(A) == 5 && A->npanels >= 2 && A->m > 0)
+    return spmv_launch_twophase(c, A, x, y, epi, u0, fin, dst);
   // mode 4: the same copy-engine all-gather, waited for as a whole, then the matrix's own plan (no per-source panels)
   const bool ce_gather = dist && c->world > 1 && sla_xwin_mode(A) == 4 && !c->skip_exchange;
   if (ce_gather) {

@@ -102,6 +102,10 @@ def p2p_exchange_mode():
         3  LL halo (symmetric halo plans): ONE kernel stores 16-byte tagged entries straight into the neighbours' halo
            buffers and unpacks the entries arriving from them — no fence, no flag round trip, no rendezvous
         4  copy-engine all-gather waited for as a whole (what 2 degrades to)
+        5  phased push (dense equal-block plans, x too large for L2 as in 2): the (#>) runs ROTATED column panels — own block,
+           then the blocks of the predecessors in groups of 1, 2, 4, ... (SLA_P2P_PANELS="1,1,2" overrides) — and group p travels
+           as TMA bulk copies issued by SLA_P2P_PUSH_CTAS one-thread CTAs on a high-priority side stream under the kernels of the
+           panels before it; rows fold panel by panel, within the same fp64 bound as 2
     Automatic (measured on B200, profiles/r02_*): 2 for dense equal-block plans on TWO ranks (cfg 2: 0.824 vs 0.933 ms, the
     exchange fully hidden), NCCL otherwise — at 8 ranks the seven copy-engine transfers per rank took 0.43 ms against 0.16 ms
     for ncclAllGather (cfg 2: 0.654 vs 0.388 ms), and the LL halo kernel only equals NCCL's grouped send/recv (11 us exposed
@@ -112,7 +116,7 @@ def p2p_exchange_mode():
     if v in ("", "auto"):
         return -1
     try:
-        return max(0, min(4, int(v)))
+        return max(0, min(5, int(v)))
     except ValueError:
         return -1
 
@@ -238,10 +242,13 @@ def distribute(ctx, A, starts):
     mode = p2p_exchange_mode()
     halo_ok = not dense and halo_eligible(starts, needs)
     if mode == -1:
-        mode = 2 if allgather and world == 2 else 0
+        n_cols = starts[-1]
+        phased_ok = (allgather and world >= 3 and 8 * n_cols > (56 << 20) and n_cols % world == 0 and (n_cols // world) % 16 == 0
+                     and all(starts[q] == q * (n_cols // world) for q in range(world + 1)))
+        mode = 2 if allgather and world == 2 else 5 if phased_ok else 0
     elif mode == 3 and not halo_ok:
         mode = 0
-    elif mode in (2, 4) and not allgather:
+    elif mode in (2, 4, 5) and not allgather:
         mode = 1
     if getattr(ctx, "p2p", False) and mode:
         lib = ctx.lib

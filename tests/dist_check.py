@@ -52,7 +52,7 @@ def main():
         xo = ora.SpVector.synth(seed + 1, n)
         y = (A @ x).toDenseListSV()
         yo = Ao.matVec(xo).toDenseListSV()
-        if getattr(A, "dist_p2p_mode", 0) == 2:
+        if getattr(A, "dist_p2p_mode", 0) in (2, 5):
             # arrival-order panels fold each row in rotated column order: a valid summation of the same products,
             # |dy_i| <= (k_i + 2) u sum_j |a_ij x_j|  (SURVEY.md section 8(d)), no longer the bit-exact ascending fold
             rp, cj, vv = Ao.toCSR()
@@ -107,7 +107,7 @@ def main():
             check(f"{name}: distributed transpose val", np.asarray(vaT).tobytes() == np.ascontiguousarray(vao[lo_:hi_], dtype=np.float64).tobytes())
             z = A.vecMat(x, out=sla.SpVector.zeroSV(r1 - r0)).toDenseListSV()
             zo = Ao.vecMat(xo).toDenseListSV()
-            if getattr(T, "dist_p2p_mode", 0) == 2:
+            if getattr(T, "dist_p2p_mode", 0) in (2, 5):
                 # the transpose has its own arrival-order exchange: rotated fold, bounded like (#>) above
                 rpt, cjt, vvt = Ao.transpose().toCSR()
                 xa = np.abs(xo.toDenseListSV())

@@ -258,7 +258,7 @@ def test_exchange_mode_env(monkeypatch):
     monkeypatch.delenv("SLA_P2P", raising=False)
     monkeypatch.delenv("SLA_P2P_X", raising=False)
     assert sd.p2p_exchange_mode() == -1
-    for v, want in (("auto", -1), ("0", 0), ("2", 2), ("3", 3), ("9", 4), ("x", -1)):
+    for v, want in (("auto", -1), ("0", 0), ("2", 2), ("3", 3), ("5", 5), ("9", 5), ("x", -1)):
         monkeypatch.setenv("SLA_P2P_X", v)
         assert sd.p2p_exchange_mode() == want
     monkeypatch.setenv("SLA_P2P", "0")
