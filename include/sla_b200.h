@@ -108,8 +108,13 @@ int        sla_p2p_enabled(const sla_ctx*);
 sla_status sla_csr_set_halo(sla_ctx*, sla_csr*, int nseg, const int64_t* base, int64_t capacity);
 sla_status sla_csr_p2p_export(sla_ctx*, sla_csr*, void* handle64);
 sla_status sla_csr_p2p_attach(sla_ctx*, sla_csr*, const void* handles /* world x 64 bytes */);
-sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on /* 0 off, 1 push kernel, 2 copy engines + arrival-order panels, 3 LL halo, 4 copy-engine all-gather */);
-int        sla_csr_p2p_mode(const sla_csr*);      /* the mode in force (2 falls back to 1 when the plan is not dense / equal-block) */
+sla_status sla_csr_p2p_enable(sla_ctx*, sla_csr*, int on /* 0 off, 1 push kernel, 2 copy engines + arrival-order panels, 3 LL halo, 4 copy-engine all-gather,
+                                                              5 phased TMA push under rotated column panels */);
+int        sla_csr_p2p_mode(const sla_csr*);      /* the mode in force (2 and 5 fall back to 4 / 1 when the plan is not dense / equal-block or x is small) */
+/* Mode 5's panel schedule, pure host arithmetic: sizes[p] (room for 8) = column blocks in panel p (panel 0 = the own block, panel
+ * p >= 1 = the next sizes[p] predecessors, exchanged in phase p); spec = "1,1,2"-style override or NULL for 1, 1, 2, 4, ...;
+ * returns the number of panels. */
+int        sla_p2p_phase_schedule(int world, const char* spec, int* sizes);
 /* transposeSM of a row-partitioned square matrix (all-to-all of entries; starts = world + 1 global row offsets, the same on
  * every rank): *out is this rank's row block of the transpose; give it an exchange plan like any block, then hand it to A
  * with sla_csr_attach_transpose so that (<#) and CGNE on the distributed A use it (A owns it afterwards). */

@@ -11,6 +11,7 @@ RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-add
 port=29520
 for variant in ${CHECKS:-auto x0 nccl}; do
   case $variant in
+    none) continue;;
     auto) ENVS="";;
     x0)   ENVS="SLA_P2P_X=0";;
     x1)   ENVS="SLA_P2P_X=1";;
@@ -27,6 +28,7 @@ for variant in ${CHECKS:-auto x0 nccl}; do
 done
 for variant in ${BENCHES:-auto x0}; do
   case $variant in
+    none) continue;;
     auto) ENVS="";;
     x0)   ENVS="SLA_P2P_X=0";;
     x4)   ENVS="SLA_P2P_X=4";;

@@ -68,6 +68,7 @@ SIGNATURES = {
     "sla_csr_p2p_attach": (C.c_int, [_p, _p, _p]),
     "sla_csr_p2p_enable": (C.c_int, [_p, _p, C.c_int]),
     "sla_csr_p2p_mode": (C.c_int, [_p]),
+    "sla_p2p_phase_schedule": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_int)]),
     "sla_vec_generate_slice": (C.c_int, [_p, _i64, _i64, C.c_uint64, _pp]),
     "sla_csr_dims": (C.c_int, [_p, _pi64, _pi64, _pi64]),
     "sla_csr_to_host": (C.c_int, [_p, _p, _pi32, _pi32, _pf64]),

@@ -521,6 +521,33 @@ extern "C" sla_status sla_csr_p2p_attach(sla_ctx* c, sla_csr* A, const void* han
   return SLA_OK;
 }
 
+// The panel schedule of the phased exchange (mode 5): sizes[p] = how many column blocks panel p holds — panel 0 the own block,
+// panel p >= 1 the next sizes[p] predecessors, whose blocks travel in phase p.  spec = "1,1,2"-style override (must start with
+// 1 and add up to world), else 1, 1, 2, 4, ...: a phase is never larger than everything multiplied before it.  Pure host
+// arithmetic (the Python planner holds the same rule: dist.phase_schedule); returns the number of panels.
+extern "C" int sla_p2p_phase_schedule(int world, const char* spec, int* sizes) {
+  if (world < 1 || !sizes) return 0;
+  int ns = 0, tot = 0;
+  const char* e = spec;
+  while (e && *e && ns < SLA_ROT_MAX) {
+    const int v = atoi(e);
+    if (v <= 0) { ns = 0; break; }
+    sizes[ns++] = v; tot += v;
+    e = strchr(e, ',');
+    if (e) ++e;
+  }
+  if (e && *e) ns = 0;                                      // more entries than panels
+  if (ns >= 2 && tot == world && sizes[0] == 1) return ns;
+  ns = 0; sizes[ns++] = 1;
+  int left = world - 1, next = 1;
+  while (left > 0) {
+    const int take = (next < left && ns < SLA_ROT_MAX - 1) ? next : left;
+    sizes[ns++] = take; left -= take;
+    next = ns == 2 ? 2 : next * 2;
+  }
+  return ns;
+}
+
 extern "C" sla_status sla_csr_p2p_enable(sla_ctx* c, sla_csr* A, int on) {
   if (!c || !A || !A->dist) return SLA_ERR_INVALID;
   sla_dist_info* d = A->dist;
@@ -567,28 +594,9 @@ extern "C" sla_status sla_csr_p2p_enable(sla_ctx* c, sla_csr* A, int on) {
       sla_rot_spec rs;
       rs.n = A->n; rs.m = A->m; rs.own_end = d->row0 + A->m; rs.P = 0; rs.kb[0] = 0;
       {
-        int sizes[SLA_ROT_MAX], ns = 0;
-        const char* e = getenv("SLA_P2P_PANELS");
-        while (e && *e && ns < SLA_ROT_MAX) {
-          const int v = atoi(e);
-          if (v <= 0) { ns = 0; break; }
-          sizes[ns++] = v;
-          e = strchr(e, ',');
-          if (e) ++e;
-        }
-        int tot = 0;
-        for (int i = 0; i < ns; ++i) tot += sizes[i];
-        if (ns < 2 || tot != W || sizes[0] != 1) {            // default: 1, 1, 2, 4, ...
-          ns = 0; sizes[ns++] = 1;
-          int left = W - 1, next = 1;
-          while (left > 0) {
-            const int take = (next < left && ns < SLA_ROT_MAX - 1) ? next : left;
-            sizes[ns++] = take; left -= take;
-            next = ns == 2 ? 2 : next * 2;
-          }
-        }
-        rs.P = ns;
-        for (int i = 0; i < ns; ++i) rs.kb[i + 1] = rs.kb[i] + sizes[i];
+        int sizes[SLA_ROT_MAX];
+        rs.P = sla_p2p_phase_schedule(W, getenv("SLA_P2P_PANELS"), sizes);
+        for (int i = 0; i < rs.P; ++i) rs.kb[i + 1] = rs.kb[i] + sizes[i];
       }
       X->nphase = rs.P;
       for (int ph = 0; ph < SLA_ROT_MAX; ++ph) X->dst_mask[ph] = X->src_mask[ph] = 0u;

@@ -85,6 +85,39 @@ def exchange_bytes(segs):
     return (8 * sum(c for d, _, _, c in segs if d == 0), 8 * sum(c for d, _, _, c in segs if d == 1))
 
 
+def phase_schedule(world, spec=None):
+    """Panel schedule of the phased x exchange (SLA_P2P_X=5; the C twin is sla_p2p_phase_schedule in csrc/p2p.cu): how many
+    column blocks each rotated panel holds — panel 0 the own block, panel p >= 1 the next predecessors, whose blocks travel in
+    phase p.  `spec` ("1,1,2") must start with 1, add up to `world` and have 2..8 entries; otherwise 1, 1, 2, 4, ...: no phase
+    is larger than everything multiplied before it."""
+    max_panels = 8
+    if spec:
+        try:
+            sizes = [int(t) for t in spec.split(",")]
+        except ValueError:
+            sizes = []
+        if 2 <= len(sizes) <= max_panels and all(v > 0 for v in sizes) and sum(sizes) == world and sizes[0] == 1:
+            return sizes
+    sizes, left, nxt = [1], world - 1, 1
+    while left > 0:
+        take = nxt if nxt < left and len(sizes) < max_panels - 1 else left
+        sizes.append(take)
+        left -= take
+        nxt = 2 if len(sizes) == 2 else nxt * 2
+    return sizes
+
+
+def phase_peers(rank, world, sizes):
+    """For each phase p of `sizes`: (ranks this rank pushes its block to, ranks whose blocks it receives).  Rank r is
+    predecessor k of rank r + k; phase p carries the predecessors sum(sizes[:p]) .. sum(sizes[:p + 1]) - 1."""
+    out, k0 = [], 0
+    for p, sz in enumerate(sizes):
+        ks = range(max(k0, 1), k0 + sz) if p else range(0)
+        out.append(([(rank + k) % world for k in ks], [(rank - k) % world for k in ks]))
+        k0 += sz
+    return out
+
+
 def p2p_wanted():
     """Peer-memory collectives (csrc/p2p.cu) are on unless SLA_P2P=0; the variable must agree on every rank."""
     return os.environ.get("SLA_P2P", "1") != "0"

@@ -263,3 +263,51 @@ def test_exchange_mode_env(monkeypatch):
         assert sd.p2p_exchange_mode() == want
     monkeypatch.setenv("SLA_P2P", "0")
     assert sd.p2p_exchange_mode() == 0
+
+
+# ---- phased x exchange (SLA_P2P_X=5): the panel schedule and who talks to whom in which phase --------------------------
+def test_phase_schedule_default():
+    assert sd.phase_schedule(2) == [1, 1]
+    assert sd.phase_schedule(3) == [1, 1, 1]
+    assert sd.phase_schedule(4) == [1, 1, 2]
+    assert sd.phase_schedule(8) == [1, 1, 2, 4]
+    assert sd.phase_schedule(16) == [1, 1, 2, 4, 8]
+    for w in range(2, 33):
+        sizes = sd.phase_schedule(w)
+        assert sum(sizes) == w and sizes[0] == 1 and len(sizes) <= 8
+        # no phase is larger than everything multiplied before it (the last of a full schedule may take the remainder)
+        if len(sizes) < 8:
+            assert all(sizes[p] <= sum(sizes[:p]) for p in range(1, len(sizes)))
+
+
+def test_phase_schedule_override_and_rejects():
+    assert sd.phase_schedule(4, "1,3") == [1, 3]
+    assert sd.phase_schedule(8, "1,1,1,1,2,2") == [1, 1, 1, 1, 2, 2]
+    for bad in ("2,2", "1,1,1", "1,0,3", "4", "1,1,1,1,1,1,1,1,1", "x"):       # not starting at 1 / wrong sum / one panel / 9 entries
+        assert sd.phase_schedule(4 if bad != "1,1,1,1,1,1,1,1,1" else 9, bad) == sd.phase_schedule(4 if bad != "1,1,1,1,1,1,1,1,1" else 9)
+
+
+def test_phase_schedule_matches_the_library():
+    import ctypes as C
+    from sparse_linear_algebra_b200 import _lib
+    L = _lib.load()
+    buf = (C.c_int * 8)()
+    for w in range(2, 17):
+        for spec in (None, "1,1,2", "1,3", "1,1,1,1,2,2", "1,7", "2,2", "1,1,1,1,1,1,1,1"):
+            n = L.sla_p2p_phase_schedule(w, spec.encode() if spec else None, buf)
+            assert list(buf[:n]) == sd.phase_schedule(w, spec), (w, spec)
+
+
+def test_phase_peers_are_consistent():
+    for w in (2, 3, 4, 5, 8, 16):
+        sizes = sd.phase_schedule(w)
+        table = [sd.phase_peers(r, w, sizes) for r in range(w)]
+        for r in range(w):
+            assert table[r][0] == ([], [])                     # panel 0 is the own block: nothing travels
+            got = []
+            for p, (send, recv) in enumerate(table[r]):
+                assert len(send) == len(recv) == (sizes[p] if p else 0)          # balanced: every rank sends what it receives
+                for q in send:
+                    assert r in table[q][p][1]                  # whoever I push to in phase p waits for me in phase p
+                got += recv
+            assert sorted(got) == [q for q in range(w) if q != r]               # every other block arrives exactly once
