@@ -115,6 +115,19 @@ int        sla_csr_p2p_mode(const sla_csr*);      /* the mode in force (2 and 5 
  * p >= 1 = the next sizes[p] predecessors, exchanged in phase p); spec = "1,1,2"-style override or NULL for 1, 1, 2, 4, ...;
  * returns the number of panels. */
 int        sla_p2p_phase_schedule(int world, const char* spec, int* sizes);
+/* Test hook, one GPU: cut an ordinary matrix into mode 5's rotated panels as if its columns were `world` equal blocks and this GPU
+ * held block `rank`; (#>) then runs panel by panel (own block first; results within the fp64 bound, not bit-identical).  world <= 1
+ * removes the panels (one pass over all columns).  sla_csr_npanels: column panels of the plan in force (0 = one pass). */
+sla_status sla_csr_debug_rot_panels(sla_ctx*, sla_csr*, int world, int rank, const char* spec);
+/* Diagnostic, one GPU (scripts/prof_push_contention.py): mode 5's push kernels copying one vector into another of the same dimension
+ * inside this GPU's memory from a high-priority side stream — start() orders the copy after what is queued on the ctx stream and
+ * returns at once, join() makes the ctx stream wait for it; kind 0 = TMA bulk kernel, 1 = LSU kernel, ctas = resident CTAs. */
+typedef struct sla_debug_push sla_debug_push;
+sla_status sla_debug_push_create(sla_ctx*, sla_vec* dst, const sla_vec* src, sla_debug_push** out);
+sla_status sla_debug_push_start(sla_ctx*, sla_debug_push*, int ctas, int kind);
+sla_status sla_debug_push_join(sla_ctx*, sla_debug_push*);
+void       sla_debug_push_free(sla_debug_push*);
+int        sla_csr_npanels(const sla_csr*);
 /* transposeSM of a row-partitioned square matrix (all-to-all of entries; starts = world + 1 global row offsets, the same on
  * every rank): *out is this rank's row block of the transpose; give it an exchange plan like any block, then hand it to A
  * with sla_csr_attach_transpose so that (<#) and CGNE on the distributed A use it (A owns it afterwards). */

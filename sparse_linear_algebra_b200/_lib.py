@@ -69,6 +69,12 @@ SIGNATURES = {
     "sla_csr_p2p_enable": (C.c_int, [_p, _p, C.c_int]),
     "sla_csr_p2p_mode": (C.c_int, [_p]),
     "sla_p2p_phase_schedule": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_int)]),
+    "sla_csr_debug_rot_panels": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_char_p]),
+    "sla_csr_npanels": (C.c_int, [_p]),
+    "sla_debug_push_create": (C.c_int, [_p, _p, _p, C.POINTER(_p)]),
+    "sla_debug_push_start": (C.c_int, [_p, _p, C.c_int, C.c_int]),
+    "sla_debug_push_join": (C.c_int, [_p, _p]),
+    "sla_debug_push_free": (None, [_p]),
     "sla_vec_generate_slice": (C.c_int, [_p, _i64, _i64, C.c_uint64, _pp]),
     "sla_csr_dims": (C.c_int, [_p, _pi64, _pi64, _pi64]),
     "sla_csr_to_host": (C.c_int, [_p, _p, _pi32, _pi32, _pf64]),

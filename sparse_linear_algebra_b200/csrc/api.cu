@@ -341,7 +341,8 @@ extern "C" sla_status sla_spmv_host(sla_ctx* c, const sla_csr* A, const double* 
   SLA_GUARD(c);
   SLA_TRY(scratch_vec(c, &c->scratch_x, csr_xdim(A)));
   SLA_TRY(scratch_vec(c, &c->scratch_y, A->m));
-  if (!A->dist && !c->spmv_tma && A->m > 0 && !getenv("SLA_HOST_NO_PIPELINE"))
+  const bool uniform_panels = A->npanels < 2 || A->panel_width > 0;     // rotated panels (test hook below) have no upload order
+  if (!A->dist && !c->spmv_tma && A->m > 0 && uniform_panels && !getenv("SLA_HOST_NO_PIPELINE"))
     return sla_spmv_host_pipelined(c, A, x_host, y_host, c->scratch_x->d, c->scratch_y->d);
   SLA_CUDA(c, cudaMemcpyAsync(c->scratch_x->d, x_host, sizeof(double) * (size_t)csr_xdim(A), cudaMemcpyHostToDevice, c->stream));
   SLA_TRY(sla_spmv(c, A, c->scratch_x, c->scratch_y));
@@ -373,3 +374,22 @@ extern "C" void sla_dense_free(sla_dense* d) {
   sla_pool_free(d->ctx, d->d, d->bytes);
   delete d;
 }
+
+// Test hook (tests/test_gpu_parity.py, one GPU): the rotated panels of the phased exchange on an ordinary matrix, as if its n columns
+// were `world` equal blocks and this GPU held block `rank` — (#>) then multiplies panel by panel, own block first.  world <= 1
+// removes the panels (one pass over all columns).
+extern "C" sla_status sla_csr_debug_rot_panels(sla_ctx* c, sla_csr* A, int world, int rank, const char* spec) {
+  if (!c || !A) return SLA_ERR_INVALID;
+  SLA_GUARD(c);
+  if (A->dist) return sla_fail(c, SLA_ERR_INVALID, "debug_rot_panels: not for row-partitioned matrices");
+  if (world <= 1) { sla_csr_free_panels(A); return SLA_OK; }
+  if (rank < 0 || rank >= world || A->n % world != 0) return sla_fail(c, SLA_ERR_INVALID, "debug_rot_panels: n must be a multiple of world, 0 <= rank < world");
+  sla_rot_spec rs;
+  int sizes[SLA_ROT_MAX];
+  rs.n = A->n; rs.m = A->n / world; rs.own_end = (long long)(rank + 1) * rs.m; rs.kb[0] = 0;
+  rs.P = sla_p2p_phase_schedule(world, spec, sizes);
+  for (int i = 0; i < rs.P; ++i) rs.kb[i + 1] = rs.kb[i] + sizes[i];
+  if (A->band) return sla_fail(c, SLA_ERR_INVALID, "debug_rot_panels: the matrix runs the band plan");
+  return sla_csr_force_rot_panels(c, A, &rs);
+}
+extern "C" int sla_csr_npanels(const sla_csr* A) { return A ? A->npanels : 0; }

@@ -448,6 +448,7 @@ sla_status sla_p2p_twophase_wait(sla_ctx* c, const sla_csr* A, int phase);
 #define SLA_ROT_MAX 8
 struct sla_rot_spec { long long n, own_end, m; int P; int kb[SLA_ROT_MAX + 1]; };
 sla_status sla_csr_force_rot_panels(sla_ctx* c, sla_csr* A, const sla_rot_spec* spec);
+extern "C" int sla_p2p_phase_schedule(int world, const char* spec, int* sizes);                  // p2p.cu
 sla_status sla_p2p_exchange_x(sla_ctx* c, const sla_csr* A, const double* x_local);
 void sla_xwin_free(sla_csr* A);
 void sla_csr_free_bsr(sla_csr* A);

@@ -521,6 +521,73 @@ extern "C" sla_status sla_csr_p2p_attach(sla_ctx* c, sla_csr* A, const void* han
   return SLA_OK;
 }
 
+// ---- diagnostic (scripts/prof_push_contention.py, ONE GPU) ------------------------------------------------------------------
+// The mode-5 push kernels copying n doubles src -> dst inside this GPU's own memory from a high-priority side stream, so that the
+// SM-side cost of a push running beside the (#>) panel kernels can be measured without a second GPU (no NVLink in the picture:
+// what is left is the CTA slots, shared memory and HBM / L2 bandwidth the push takes from the panel kernels).
+struct sla_debug_push {
+  cudaStream_t side; cudaEvent_t ev0, ev1;
+  p2p_item* d_items; char** d_peer; unsigned int* d_ticket; int nitems; const double* src;
+};
+extern "C" sla_status sla_debug_push_create(sla_ctx* c, sla_vec* dstv, const sla_vec* srcv, sla_debug_push** out) {
+  if (!c || !dstv || !srcv || !out || dstv->n != srcv->n || srcv->n < 2) return SLA_ERR_INVALID;
+  SLA_GUARD(c);
+  double* dst = dstv->d;
+  const double* src = srcv->d;
+  const int64_t n = srcv->n & ~(int64_t)1;
+  sla_debug_push* h = new sla_debug_push();
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  std::vector<p2p_item> items;
+  for (int64_t o = 0; o < n; o += P2P_BULK_LEN) {
+    p2p_item it; it.peer = 0; it.len = (int)(n - o < P2P_BULK_LEN ? n - o : P2P_BULK_LEN); it.goff = o; it.src = o;
+    items.push_back(it);
+  }
+  h->nitems = (int)items.size(); h->src = src;
+  char* peer0 = reinterpret_cast<char*>(dst);
+  cudaError_t e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev0, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev1, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_items, sizeof(p2p_item) * items.size());
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_peer, sizeof(char*));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_items, items.data(), sizeof(p2p_item) * items.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_peer, &peer0, sizeof(char*), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_push_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2P_BULK_STAGES * P2P_BULK_BYTES);
+  if (e != cudaSuccess) { cudaGetLastError(); return sla_fail(c, SLA_ERR_CUDA, "debug_push_create: CUDA error"); }
+  *out = h;
+  return SLA_OK;
+}
+// starts the copy on the side stream once everything already queued on the ctx stream is done; kind 0 = TMA bulk kernel, 1 = LSU kernel
+extern "C" sla_status sla_debug_push_start(sla_ctx* c, sla_debug_push* h, int ctas, int kind) {
+  if (!c || !h || ctas <= 0) return SLA_ERR_INVALID;
+  SLA_GUARD(c);
+  SLA_CUDA(c, cudaEventRecord(h->ev0, c->stream));
+  SLA_CUDA(c, cudaStreamWaitEvent(h->side, h->ev0, 0));
+  const int grid = ctas < h->nitems ? ctas : h->nitems;
+  if (kind == 0)
+    p2p_push_bulk_kernel<<<grid, 32, P2P_BULK_STAGES * P2P_BULK_BYTES, h->side>>>(h->d_items, h->nitems, h->d_peer, 0, h->src, 0, 1, 0u, 1ull, h->d_ticket);
+  else
+    p2p_push_phase_kernel<<<grid, P2P_PUSH_THREADS, 0, h->side>>>(h->d_items, h->nitems, h->d_peer, 0, h->src, 0, 1, 0u, 1ull, h->d_ticket);
+  SLA_LAUNCH_CHECK(c);
+  SLA_CUDA(c, cudaEventRecord(h->ev1, h->side));
+  return SLA_OK;
+}
+// the ctx stream waits for the copy started last
+extern "C" sla_status sla_debug_push_join(sla_ctx* c, sla_debug_push* h) {
+  if (!c || !h) return SLA_ERR_INVALID;
+  SLA_CUDA(c, cudaStreamWaitEvent(c->stream, h->ev1, 0));
+  return SLA_OK;
+}
+extern "C" void sla_debug_push_free(sla_debug_push* h) {
+  if (!h) return;
+  cudaStreamSynchronize(h->side);
+  cudaStreamDestroy(h->side); cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaFree(h->d_items); cudaFree(h->d_peer); cudaFree(h->d_ticket);
+  delete h;
+}
+
 // The panel schedule of the phased exchange (mode 5): sizes[p] = how many column blocks panel p holds — panel 0 the own block,
 // panel p >= 1 the next sizes[p] predecessors, whose blocks travel in phase p.  spec = "1,1,2"-style override (must start with
 // 1 and add up to world), else 1, 1, 2, 4, ...: a phase is never larger than everything multiplied before it.  Pure host

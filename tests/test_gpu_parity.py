@@ -8,6 +8,8 @@ Tolerances, u = 2^-53:
   * dot / norm: |d| <= 64 u sum|x_i y_i| (tree reduction).
   * Krylov iterates: first steps within 1e-10 relative of the oracle trajectory; same iteration count.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -831,3 +833,60 @@ def test_spmv_band_plan_bit_exact(sla, o, monkeypatch, R, W):
     # (#>) is bit-identical either way; the fused dots are reduced over a different grid, so the iterates agree to rounding
     np.testing.assert_allclose(xs[0], xs[2], rtol=1e-10, atol=1e-13)
     assert xs[1][0] == xs[3][0] and abs(xs[1][1] - xs[3][1]) <= 1e-8 * max(abs(xs[3][1]), 1e-300)
+
+
+# =============================================================== round 2: rotated column panels of the phased x exchange (p2p.cu mode 5)
+@pytest.mark.parametrize("world,spec", [(2, None), (4, None), (4, "1,3"), (8, None), (8, "1,1,1,1,2,2"), (5, "1,2,2")])
+def test_spmv_rotated_panels_single_gpu(sla, o, world, spec):
+    """The panel builder behind SLA_P2P_X=5, exercised on ONE GPU through the test hook: the matrix is cut as if its columns were
+    `world` equal blocks and this GPU held block `rank`; (#>) then folds each row panel by panel, own block first.  Every entry
+    must land in exactly one panel (checked through the result: each row within (k + 2) u sum |a_ij x_j| of the oracle's left
+    fold, rows living in a single panel bit-exact), for every rank's rotation, wrap-around included."""
+    ctx = sla.default_context()
+    rng = np.random.default_rng(1000 + world)
+    n = 40 * world                                           # 40 columns per block
+    m = 333
+    i, j, v = _rand_coo(rng, m, n, 9000, long_rows=((0, min(n, 200)),))      # every row <= 256 entries: the one-pass product is bit-exact
+    # rows 1..10 live entirely inside one column block each: one panel only, so they stay bit-exact under any rotation
+    keep = ~((i >= 1) & (i <= 10))
+    i, j, v = i[keep], j[keep], v[keep]
+    for r in range(1, 11):
+        blk = (r * 3) % world
+        cols = np.sort(rng.choice(40, size=17, replace=False)) + 40 * blk
+        i = np.concatenate([i, np.full(17, r)]); j = np.concatenate([j, cols]); v = np.concatenate([v, rng.standard_normal(17)])
+    x = rng.standard_normal(n)
+    Ao = o.SpMatrix.fromCOO((m, n), i, j, v)
+    yo = Ao.matVec(o.SpVector.mkSpVR(n, x)).toDenseListSV()
+    rp, cj, vv = Ao.toCSR()
+    mag = np.add.reduceat(np.abs(vv) * np.abs(x)[cj], rp[:-1])
+    mag[np.diff(rp) == 0] = 0.0
+    bound = (np.diff(rp) + 2) * 2.0 ** -53 * mag
+    sizes = (C.c_int * 8)()
+    npan = ctx.lib.sla_p2p_phase_schedule(world, spec.encode() if spec else None, sizes)
+    xs = sla.SpVector.mkSpVR(n, x)
+    for rank in range(world):
+        A = sla.SpMatrix.fromCOO((m, n), i, j, v)
+        base = (A @ xs).toDenseListSV()
+        assert base.tobytes() == yo.tobytes()
+        ctx.check(ctx.lib.sla_csr_debug_rot_panels(ctx.h, A.h, world, rank, spec.encode() if spec else None))
+        assert ctx.lib.sla_csr_npanels(A.h) == npan
+        y = (A @ xs).toDenseListSV()
+        assert np.all(np.abs(y - yo) <= bound), (world, spec, rank, float(np.max(np.abs(y - yo) / np.maximum(bound, 1e-300))))
+        assert y[1:11].tobytes() == yo[1:11].tobytes(), (world, spec, rank)
+        ctx.check(ctx.lib.sla_csr_debug_rot_panels(ctx.h, A.h, 1, 0, None))       # panels off again: one pass, bit-exact
+        assert ctx.lib.sla_csr_npanels(A.h) == 0
+        assert (A @ xs).toDenseListSV().tobytes() == yo.tobytes()
+    # a Krylov trajectory on rotated panels (the fused dot epilogues ride on the LAST panel's launch)
+    nk = 4096
+    A = sla.SpMatrix.generate(sla.GEN_UNIFORM, nk, 16, 0x5EED0041)
+    b = A @ sla.SpVector.generate(nk, 0x5EED0042)
+    traj = []
+    for rot in (False, True):
+        if rot:
+            ctx.check(ctx.lib.sla_csr_debug_rot_panels(ctx.h, A.h, world if nk % world == 0 else 4, 1, None))
+        st = sla.bicgsInit(A, b, sla.SpVector.zeroSV(nk))
+        rhat = st.r.copy()
+        for _ in range(5):
+            sla.bicgstabStep(A, rhat, st)
+        traj.append(st.x.toDenseListSV())
+    assert np.allclose(traj[0], traj[1], rtol=1e-9, atol=1e-12)
