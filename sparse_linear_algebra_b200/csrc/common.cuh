@@ -441,7 +441,7 @@ int sla_xwin_mode(const sla_csr* A);                                            
 sla_status sla_p2p_arrival_begin(sla_ctx* c, const sla_csr* A, const double* x_local);
 sla_status sla_p2p_arrival_wait(sla_ctx* c, const sla_csr* A, int src);
 sla_status sla_p2p_arrival_end(sla_ctx* c);
-sla_status sla_p2p_twophase_begin(sla_ctx* c, const sla_csr* A, const double* x_local);          // mode 5
+sla_status sla_p2p_twophase_begin(sla_ctx* c, const sla_csr* A, const double* x_local);          // mode 5 (phased push; named after its first, two-phase form)
 sla_status sla_p2p_twophase_wait(sla_ctx* c, const sla_csr* A, int phase);
 // Rotated column panels of a row-partitioned matrix with equal blocks (spmv.cu): column j belongs to the block of predecessor
 // k = ((own_end - 1 - j) mod n) / m of this rank (k = 0: own block); panel p holds the predecessors kb[p] <= k < kb[p + 1].

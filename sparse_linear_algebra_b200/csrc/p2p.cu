@@ -61,7 +61,7 @@ struct sla_xwin {                                // per distributed matrix: [256
   p2p_item* d_items;
   int nitems;                                    // send items; LL windows: followed by nrecv unpack items
   int nrecv;
-  // mode 5 (two-phase push): the send items re-ordered by phase, the peers / sources of each phase
+  // mode 5 (phased push): the send items cut into ring-buffer pieces and ordered by phase, the destinations / sources of each phase
   p2p_item* d_items2; int nphase, n_phase[SLA_ROT_MAX]; unsigned dst_mask[SLA_ROT_MAX], src_mask[SLA_ROT_MAX]; unsigned int* d_ticket2; int push_ctas, bulk;
   unsigned int* d_ticket;
   unsigned long long seq;
@@ -529,6 +529,7 @@ struct sla_debug_push {
   cudaStream_t side; cudaEvent_t ev0, ev1;
   p2p_item* d_items; char** d_peer; unsigned int* d_ticket; int nitems; const double* src;
 };
+extern "C" void sla_debug_push_free(sla_debug_push* h);
 extern "C" sla_status sla_debug_push_create(sla_ctx* c, sla_vec* dstv, const sla_vec* srcv, sla_debug_push** out) {
   if (!c || !dstv || !srcv || !out || dstv->n != srcv->n || srcv->n < 2) return SLA_ERR_INVALID;
   SLA_GUARD(c);
@@ -555,7 +556,7 @@ extern "C" sla_status sla_debug_push_create(sla_ctx* c, sla_vec* dstv, const sla
   if (e == cudaSuccess) e = cudaMemcpy(h->d_peer, &peer0, sizeof(char*), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(p2p_push_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2P_BULK_STAGES * P2P_BULK_BYTES);
-  if (e != cudaSuccess) { cudaGetLastError(); return sla_fail(c, SLA_ERR_CUDA, "debug_push_create: CUDA error"); }
+  if (e != cudaSuccess) { cudaGetLastError(); sla_debug_push_free(h); return sla_fail(c, SLA_ERR_CUDA, "debug_push_create: CUDA error"); }
   *out = h;
   return SLA_OK;
 }
@@ -582,8 +583,9 @@ extern "C" sla_status sla_debug_push_join(sla_ctx* c, sla_debug_push* h) {
 }
 extern "C" void sla_debug_push_free(sla_debug_push* h) {
   if (!h) return;
-  cudaStreamSynchronize(h->side);
-  cudaStreamDestroy(h->side); cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   cudaFree(h->d_items); cudaFree(h->d_peer); cudaFree(h->d_ticket);
   delete h;
 }
