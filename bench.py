@@ -423,6 +423,31 @@ def run_gpu(args):
         msb, _ = timed(lambda: B.matVec(x, out=y), args.steps, args.warmup)
         extra["spmv_banded_gbs"] = nbytes / (msb * 1e-3) / 1e9
         extra["spmv_banded_ms"] = msb
+        if world == 1:
+            # the same matrix under the opt-in sliced-ELL band plan (x staged through shared memory, csrc/spmv_bandsell.cuh): timed, and
+            # its result compared bit for bit with the tile kernel's on all n rows.  Never allowed to break the line.
+            try:
+                yb_ref = y.toDenseListSV()
+                prev = os.environ.get("SLA_SPMV_BAND")
+                os.environ["SLA_SPMV_BAND"] = "3"
+                try:
+                    t0 = time.perf_counter()
+                    Bs = gen(sla.GEN_BANDED, n, k, SEED_CFG2, 65536)
+                    ctx.sync()
+                    build_s = time.perf_counter() - t0
+                finally:
+                    if prev is None:
+                        os.environ.pop("SLA_SPMV_BAND", None)
+                    else:
+                        os.environ["SLA_SPMV_BAND"] = prev
+                ys = sla.SpVector.zeroSV(n)
+                mss, _ = timed(lambda: Bs.matVec(x, out=ys), args.steps, args.warmup)
+                extra["spmv_banded_sell"] = {"ms": mss, "gbs": nbytes / (mss * 1e-3) / 1e9, "frac": nbytes / (mss * 1e-3) / 1e9 / load_peak()[0],
+                                             "plan_build_s": build_s, "bit_identical_to_tile_kernel": ys.toDenseListSV().tobytes() == yb_ref.tobytes(),
+                                             "how": "SLA_SPMV_BAND=3 (opt-in): sliced-ELL cells, x in shared memory, a thread per row"}
+                del Bs, ys
+            except Exception as exc:                        # noqa: BLE001 - context number only
+                extra["spmv_banded_sell"] = {"error": str(exc)[:200]}
         del B
     if "cfg3" in want:
         # ---- config 3: BiCGSTAB on the 5-point Laplacian 4096^2, fixed number of bicgstabStep calls

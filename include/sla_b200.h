@@ -122,6 +122,12 @@ sla_status sla_csr_debug_rot_panels(sla_ctx*, sla_csr*, int world, int rank, con
 /* Diagnostic, one GPU (scripts/prof_push_contention.py): mode 5's push kernels copying one vector into another of the same dimension
  * inside this GPU's memory from a high-priority side stream — start() orders the copy after what is queued on the ctx stream and
  * returns at once, join() makes the ctx stream wait for it; kind 0 = TMA bulk kernel, 1 = LSU kernel, ctas = resident CTAs. */
+/* Host-only twin of the sliced-ELL band plan (csrc/spmv_bandsell.cuh; SLA_SPMV_BAND=3): builds the plan for a HOST CSR (int32
+ * indices, columns ascending inside a row) and runs the kernel's loop nest on the CPU — no GPU, no context.  Test infrastructure for the
+ * layout and the summation order.  stats[5] = cells, padded entries, descriptors, largest cell count of a row block, slices.
+ * Returns 0; 1 when the matrix does not fit the plan; 2 on bad arguments. */
+int        sla_debug_bsell_host(int m, int64_t n, const int32_t* row_ptr, const int32_t* col, const double* val, int R, int W, int threads,
+                                const double* x, double* y, int64_t* stats);
 typedef struct sla_debug_push sla_debug_push;
 sla_status sla_debug_push_create(sla_ctx*, sla_vec* dst, const sla_vec* src, sla_debug_push** out);
 sla_status sla_debug_push_start(sla_ctx*, sla_debug_push*, int ctas, int kind);

@@ -71,6 +71,7 @@ SIGNATURES = {
     "sla_p2p_phase_schedule": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_int)]),
     "sla_csr_debug_rot_panels": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_char_p]),
     "sla_csr_npanels": (C.c_int, [_p]),
+    "sla_debug_bsell_host": (C.c_int, [C.c_int, _i64, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
     "sla_debug_push_create": (C.c_int, [_p, _p, _p, C.POINTER(_p)]),
     "sla_debug_push_start": (C.c_int, [_p, _p, C.c_int, C.c_int]),
     "sla_debug_push_join": (C.c_int, [_p, _p]),

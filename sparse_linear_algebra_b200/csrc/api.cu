@@ -36,6 +36,7 @@ static sla_status ctx_create(int device, int rank, int world, sla_ctx** out) {
   if (const char* h = getenv("SLA_SPMV_HINTS")) c->spmv_hints = atoi(h);
   if (const char* h = getenv("SLA_SPMV_TMA")) c->spmv_tma = atoi(h);
   if (const char* h = getenv("SLA_SPMV_BULK")) c->spmv_bulk = atoi(h);
+  if (const char* h = getenv("SLA_BSELL_VARIANT")) c->bsell_variant = atoi(h);
   cudaError_t ce = cudaSetDevice(device);
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreate(&c->ev0);
@@ -114,6 +115,7 @@ extern "C" sla_status sla_set_option(sla_ctx* c, const char* name, int64_t value
   if (strcmp(name, "skip_exchange") == 0) { c->skip_exchange = value != 0; return SLA_OK; }
   if (strcmp(name, "spmv_hints") == 0) { c->spmv_hints = (int)value; return SLA_OK; }
   if (strcmp(name, "spmv_bulk") == 0) { c->spmv_bulk = value != 0; return SLA_OK; }
+  if (strcmp(name, "bsell_variant") == 0) { c->bsell_variant = value; return SLA_OK; }
   return sla_fail(c, SLA_ERR_INVALID, "sla_set_option: unknown option");
 }
 

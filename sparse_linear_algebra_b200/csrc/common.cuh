@@ -45,6 +45,7 @@ struct sla_ctx {
   int spmv_hints;            // bit0: matrix stream L2 evict_first, bit1: x gathers L2 evict_last (env SLA_SPMV_HINTS)
   cudaStream_t copy_stream;  // PCIe copies of the pipelined host-buffer (#>) (spmv.cu)
   cudaEvent_t ev_copy[SLA_MAX_PANELS + 16];
+  int bsell_variant;         // launch shape of the sliced-ELL band kernel (spmv_bandsell.cuh; env SLA_BSELL_VARIANT / option "bsell_variant")
   int spmv_bulk;             // 1: the tile kernel stages its (col, val) tile with bulk copies instead of LDG (env SLA_SPMV_BULK / option "spmv_bulk")
   int spmv_tma;              // 0: LDG tile kernel; k > 0: TMA-staged persistent kernel with k CTAs per SM (env SLA_SPMV_TMA)
   const void* scal_owner;    // Krylov state whose recurrence scalars currently live in scal[]

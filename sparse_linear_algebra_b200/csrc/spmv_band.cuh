@@ -39,7 +39,9 @@
 #define BAND_PAD_META 0xFFFFFFFFu           // padding entry (never a real one: local row 65535 would need R = 65536)
 #define BAND_MAX_SP 1024                    // sub-panels per row block (shared-memory table)
 
+struct sla_bsell_dev;                       // spmv_bandsell.cuh: the sliced-ELL form of the plan
 struct sla_band_plan {
+  sla_bsell_dev* sell;  // non-null: the plan is the sliced-ELL one and nothing below is used
   int R, W, nrb;
   int* win_lo;          // nrb      first column of the block's window (even)
   int* sp_base;         // nrb + 1  global sub-panel index of the block's first sub-panel
@@ -49,6 +51,8 @@ struct sla_band_plan {
   int64_t nent;         // padded entry count
   int nsp;
 };
+
+#include "spmv_bandsell.cuh"
 
 struct BandArgs {
   const int* win_lo; const int* sp_base; const int* seg_off; const double* val; const unsigned* meta;
@@ -278,6 +282,7 @@ __global__ void band_windows_kernel(const int* __restrict__ cmin, const int* __r
 void sla_csr_free_band(sla_csr* A) {
   sla_band_plan* B = (sla_band_plan*)A->band;
   if (!B) return;
+  bsell_free_dev(B->sell);
   cudaFree(B->win_lo); cudaFree(B->sp_base); cudaFree(B->seg_off); cudaFree(B->val); cudaFree(B->meta);
   delete B;
   A->band = nullptr;
@@ -300,6 +305,51 @@ static sla_status build_band_plan(sla_ctx* c, sla_csr* A) {
   int want = 0;
   if (const char* e = getenv("SLA_SPMV_BAND")) want = atoi(e);
   if (want <= 0 || A->dist || A->m == 0 || A->nnz == 0 || A->n >= (1LL << 31) - 2) return SLA_OK;
+  if (want == 3 || want == 4) {
+    // sliced-ELL form (spmv_bandsell.cuh), built on the host; 4 = with the automatic test
+    if (want == 4 && A->nnz < (1 << 20)) return SLA_OK;
+    int R = 8192, W = 8192;
+    if (const char* e = getenv("SLA_BAND_R")) R = atoi(e);
+    if (const char* e = getenv("SLA_BAND_W")) W = atoi(e);
+    if (R < 32 || R > 32768 || W < 32 || W > 32768 || (W & 1) || bsell_smem_bytes(R, W) > 227u * 1024u - 1024u)
+      return sla_fail(c, SLA_ERR_INVALID, "band plan: SLA_BAND_R / SLA_BAND_W out of range");
+    // a cheap look at the column windows on the device before the matrix is copied to the host for the conversion
+    {
+      const int m = (int)A->m, nrb = (m + R - 1) / R;
+      int *cmin = nullptr, *cmax = nullptr;
+      if (cudaMalloc(&cmin, sizeof(int) * nrb) != cudaSuccess || cudaMalloc(&cmax, sizeof(int) * nrb) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(cmin); return SLA_OK;
+      }
+      band_range_kernel<<<nrb, 256, 0, c->stream>>>(A->row_ptr, A->col, m, R, cmin, cmax);
+      c->launches++;
+      std::vector<int> hmin(nrb), hmax(nrb);
+      cudaMemcpyAsync(hmin.data(), cmin, sizeof(int) * nrb, cudaMemcpyDeviceToHost, c->stream);
+      cudaMemcpyAsync(hmax.data(), cmax, sizeof(int) * nrb, cudaMemcpyDeviceToHost, c->stream);
+      const cudaError_t e = cudaStreamSynchronize(c->stream);
+      cudaFree(cmin); cudaFree(cmax);
+      if (e != cudaSuccess) return sla_fail(c, SLA_ERR_CUDA, "band plan: CUDA error");
+      long long cells = 0; int worst = 0;
+      for (int rb = 0; rb < nrb; ++rb) {
+        if (hmax[rb] < hmin[rb]) continue;
+        const int nc = hmax[rb] / W - hmin[rb] / W + 1;
+        cells += nc; worst = nc > worst ? nc : worst;
+      }
+      if (worst > BSELL_MAX_CELLS) return SLA_OK;                                        // not a banded matrix
+      if (want == 4) {
+        if (8.0 * W * (double)cells > 0.5 * 12.0 * (double)A->nnz) return SLA_OK;          // staging x would cost more than half the entry stream
+        if (cells < 4LL * nrb) return SLA_OK;        // a narrow band: the tile kernel's gathers already hit L1 / L2 lines (cfg 3: 82 %)
+      }
+    }
+    sla_bsell_dev* D = nullptr;
+    SLA_TRY(bsell_build_dev(c, A, R, W, want == 4, &D));
+    if (!D) return SLA_OK;
+    sla_band_plan* B = new (std::nothrow) sla_band_plan();
+    if (!B) { bsell_free_dev(D); return sla_fail(c, SLA_ERR_ALLOC, "band plan alloc"); }
+    memset(B, 0, sizeof(*B));
+    B->sell = D; B->R = R; B->W = W; B->nrb = D->nrb;
+    A->band = B;
+    return SLA_OK;
+  }
   if (want == 2) { want = -1; if (A->nnz < (1 << 20)) return SLA_OK; }
   int R = 8192, W = 4096;
   if (const char* e = getenv("SLA_BAND_R")) R = atoi(e);
@@ -415,6 +465,7 @@ static sla_status band_launch_epi(sla_ctx* c, const sla_csr* A, const double* x,
 }
 
 static sla_status band_launch(sla_ctx* c, const sla_csr* A, const double* x, double* y, int epi, const double* u0, int fin, int dst) {
+  if (((const sla_band_plan*)A->band)->sell) return bsell_launch(c, A, ((const sla_band_plan*)A->band)->sell, x, y, epi, u0, fin, dst);
   switch (epi) {
     case EPI_NONE:    return band_launch_epi<EPI_NONE>(c, A, x, y, u0, fin, dst);
     case EPI_DOT1:    return band_launch_epi<EPI_DOT1>(c, A, x, y, u0, fin, dst);

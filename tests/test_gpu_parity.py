@@ -780,12 +780,14 @@ def test_spmv_bulk_staging_bit_exact(sla, o, monkeypatch):
 
 # =============================================================== round 2: x staged through shared memory (band plan, spmv_band.cuh)
 
-@pytest.mark.parametrize("R,W", [("64", "32"), ("16", "16"), ("4096", "1024"), ("8192", "4096")])
-def test_spmv_band_plan_bit_exact(sla, o, monkeypatch, R, W):
-    """The band plan (row blocks x column sub-panels, x in shared memory, SLA_SPMV_BAND=1 forces it at any size) gives the
-    same bits as the oracle's left fold: banded, stencil, a narrow random matrix with empty rows, long rows (any length is
-    exact here), ragged sizes, odd n; with the Krylov epilogues riding on it (dots: tolerance, another reduction grid)."""
-    monkeypatch.setenv("SLA_SPMV_BAND", "1")
+@pytest.mark.parametrize("form,R,W", [("1", "64", "32"), ("1", "16", "16"), ("1", "4096", "1024"), ("1", "8192", "4096"),
+                                      ("3", "64", "32"), ("3", "32", "32"), ("3", "4096", "1024"), ("3", "8192", "8192")])
+def test_spmv_band_plan_bit_exact(sla, o, monkeypatch, form, R, W):
+    """The band plans (row blocks x column sub-panels, x in shared memory; SLA_SPMV_BAND=1: entry-sorted stream, spmv_band.cuh;
+    =3: sliced-ELL cells with a thread per row, spmv_bandsell.cuh — both forced at any size here) give the same bits as the
+    oracle's left fold: banded, stencil, a narrow random matrix with empty rows, long rows (any length is exact here), ragged
+    sizes, odd n; with the Krylov epilogues riding on it (dots: tolerance, another reduction grid)."""
+    monkeypatch.setenv("SLA_SPMV_BAND", form)
     monkeypatch.setenv("SLA_BAND_R", R)
     monkeypatch.setenv("SLA_BAND_W", W)
     seed = 0x5EED0051
@@ -819,7 +821,7 @@ def test_spmv_band_plan_bit_exact(sla, o, monkeypatch, R, W):
     # a BiCGSTAB trajectory on the banded family: same bits with and without the band plan
     n, k = 20000, 12
     xs = []
-    for bandplan in ("1", "0"):
+    for bandplan in (form, "0"):
         monkeypatch.setenv("SLA_SPMV_BAND", bandplan)
         A = sla.SpMatrix.generate(sla.GEN_BANDED, n, k, seed, 200)
         b = A @ sla.SpVector.generate(n, seed + 2)
