@@ -5,7 +5,8 @@
 * an interleaving model of the two device protocols (double-buffered by sequence parity, monotone flags, "wait
   until flag >= seq"): a randomised scheduler steps `world` simulated ranks one memory operation at a time and the
   test asserts that no rank ever reads a contribution that is not the one of its current collective — the
-  write-after-read argument in the header of p2p.cu, executed.
+  write-after-read argument in the header of p2p.cu, executed — for the all-reduce, the push exchange, the copy-engine exchange
+  consumed in arrival order (mode 2) and the phased push under rotated panels (mode 5).
 """
 import os
 import random
@@ -221,3 +222,61 @@ def test_arrival_order_protocol_model(world):
             assert [s for s, _ in outs[r]] == list(range(1, nex + 1))
             for seq, got in outs[r]:
                 assert got == {t: (t + 1) * 1000 + seq for t in range(world) if t != r}, f"rank {r}, exchange {seq}"
+
+
+# ---- mode 5 (phased push under rotated column panels): compute stream = record "x is final", then per panel p a wait on the flags of
+# phase p's sources followed by the panel kernel reading exactly those blocks, then a wait for the own pushes (x_local may be overwritten
+# afterwards); comm stream = after the event, per phase: the blocks to the phase's destinations, then (last CTA) the flags on them.
+
+def _phased_compute(rank, world, nex, win, ev, done, peers, out):
+    for seq in range(1, nex + 1):
+        ev[rank] = seq                                   # cudaEventRecord(ev_x0): the panel kernels of seq - 1 are done
+        yield
+        b = seq & 1
+        got = {}
+        for _send, recv in peers:                        # panel p (panel 0: own block, nothing to wait for)
+            for src in recv:
+                while win[rank]["flag"][src] < seq:      # p2p_wait_kernel on the phase's source flags
+                    yield
+            for src in recv:
+                got[src] = win[rank]["buf"][b][src]      # the panel kernel gathering from those blocks
+                yield
+        while done[rank] < seq:                          # sla_p2p_arrival_end: my pushes have read x_local
+            yield
+        out.append((seq, got))
+
+
+def _phased_comm(rank, world, nex, win, ev, done, peers):
+    for seq in range(1, nex + 1):
+        while ev[rank] < seq:                            # cudaStreamWaitEvent(comm_stream, ev_x0)
+            yield
+        b = seq & 1
+        for send, _recv in peers:                        # one push kernel per phase
+            for q in send:
+                win[q]["buf"][b][rank] = (rank + 1) * 1000 + seq
+                yield
+            for q in send:
+                win[q]["flag"][rank] = seq               # raised by the last CTA, after every piece of the phase
+                yield
+        done[rank] = seq
+
+
+@pytest.mark.parametrize("world,spec", [(2, None), (3, None), (4, None), (4, "1,3"), (8, None), (8, "1,1,1,1,2,2"), (8, "1,1,1,1,1,1,1,1")])
+def test_phased_push_protocol_model(world, spec):
+    from sparse_linear_algebra_b200 import dist as sd
+
+    sizes = sd.phase_schedule(world, spec)
+    for seed in range(30):
+        rng = random.Random(seed * 389 + world)
+        nex = 8
+        win = [{"buf": [[None] * world for _ in range(2)], "flag": [0] * world} for _ in range(world)]
+        ev, done = [0] * world, [0] * world
+        outs = [[] for _ in range(world)]
+        tables = [sd.phase_peers(r, world, sizes) for r in range(world)]
+        gens = [_phased_compute(r, world, nex, win, ev, done, tables[r], outs[r]) for r in range(world)]
+        gens += [_phased_comm(r, world, nex, win, ev, done, tables[r]) for r in range(world)]
+        _run(gens, rng)
+        for r in range(world):
+            assert [s for s, _ in outs[r]] == list(range(1, nex + 1))
+            for seq, got in outs[r]:
+                assert got == {t: (t + 1) * 1000 + seq for t in range(world) if t != r}, f"rank {r}, exchange {seq}, schedule {sizes}"
