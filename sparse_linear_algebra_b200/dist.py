@@ -118,6 +118,21 @@ def phase_peers(rank, world, sizes):
     return out
 
 
+def auto_exchange_mode(allgather, world, starts):
+    """The automatic transport of the x exchange (SLA_P2P_X unset), from global quantities only so that every rank decides alike:
+    2 (copy engines, arrival order) for dense equal-block plans on two ranks; 5 (phased TMA push under rotated column panels) from three
+    ranks on when the plan is dense, the blocks are equal, in rank order and a multiple of 16 rows, and x (8 n bytes) exceeds what stays
+    L2-resident (56 MB: the matrices the single-GPU plan column-panelises anyway); NCCL (0) otherwise.  Measured: DESIGN.md section 5."""
+    if not allgather:
+        return 0
+    if world == 2:
+        return 2
+    n_cols = starts[-1]
+    block = n_cols // world if world else 0
+    equal = world >= 3 and n_cols % world == 0 and block % 16 == 0 and all(starts[q] == q * block for q in range(world + 1))
+    return 5 if equal and 8 * n_cols > (56 << 20) else 0
+
+
 def p2p_wanted():
     """Peer-memory collectives (csrc/p2p.cu) are on unless SLA_P2P=0; the variable must agree on every rank."""
     return os.environ.get("SLA_P2P", "1") != "0"
@@ -275,10 +290,7 @@ def distribute(ctx, A, starts):
     mode = p2p_exchange_mode()
     halo_ok = not dense and halo_eligible(starts, needs)
     if mode == -1:
-        n_cols = starts[-1]
-        phased_ok = (allgather and world >= 3 and 8 * n_cols > (56 << 20) and n_cols % world == 0 and (n_cols // world) % 16 == 0
-                     and all(starts[q] == q * (n_cols // world) for q in range(world + 1)))
-        mode = 2 if allgather and world == 2 else 5 if phased_ok else 0
+        mode = auto_exchange_mode(allgather, world, starts)
     elif mode == 3 and not halo_ok:
         mode = 0
     elif mode in (2, 4, 5) and not allgather:

@@ -311,3 +311,16 @@ def test_phase_peers_are_consistent():
                     assert r in table[q][p][1]                  # whoever I push to in phase p waits for me in phase p
                 got += recv
             assert sorted(got) == [q for q in range(w) if q != r]               # every other block arrives exactly once
+
+
+def test_auto_exchange_mode_policy():
+    n = 10_000_000
+    eq = lambda w, n_=n: [q * (n_ // w) for q in range(w + 1)]
+    assert sd.auto_exchange_mode(True, 2, eq(2)) == 2                      # two ranks: copy engines in arrival order
+    assert sd.auto_exchange_mode(True, 4, eq(4)) == 5 and sd.auto_exchange_mode(True, 8, eq(8)) == 5      # cfg 2 at 4 and 8 ranks
+    assert sd.auto_exchange_mode(False, 8, eq(8)) == 0                     # halo plans (cfg 3, banded): NCCL send/recv
+    assert sd.auto_exchange_mode(True, 8, eq(8, 4_000_000)) == 0           # cfg 4: x (32 MB) stays in L2, panels would cost more than they hide
+    assert sd.auto_exchange_mode(True, 3, [0, 3_333_334, 6_666_667, 10_000_000]) == 0      # unequal blocks
+    assert sd.auto_exchange_mode(True, 4, [0, 2_500_000, 5_000_000, 7_500_016, 10_000_000]) == 0
+    assert sd.auto_exchange_mode(True, 5, eq(5, 10_000_040)) == 0          # blocks of 2 000 008 rows: a multiple of 8, not of 16
+    assert sd.auto_exchange_mode(True, 16, eq(16, 16_000_000)) == 5
