@@ -204,6 +204,12 @@ class KrylovState {
   SpVector p() const { return field(SLA_FIELD_P); }
   SpVector u() const { return field(SLA_FIELD_U); }
   sla_krylov* get() const { return st_.get(); }
+  // deep copy: what a PURE step needs (`iterate (bicgstabStep aa r0hat) st0 !! 20` keeps st0 usable, README.md:208)
+  KrylovState clone() const {
+    sla_krylov* out = nullptr;
+    c_.check(sla_krylov_clone(c_.get(), st_.get(), &out));
+    return KrylovState(c_, out);
+  }
 
  private:
   Context c_;
@@ -218,6 +224,12 @@ inline KrylovState bicgsInit(const SpMatrix& aa, const SpVector& b, const SpVect
 inline KrylovState& bicgstabStep(const SpMatrix& aa, const SpVector& r0hat, KrylovState& st) {
   aa.ctx().check(sla_bicgstab_step(aa.ctx().get(), aa.get(), r0hat.get(), st.get()));
   return st;
+}
+// the reference's signature: a new record, the argument untouched (clone, then advance the clone)
+inline KrylovState bicgstabStepPure(const SpMatrix& aa, const SpVector& r0hat, const KrylovState& st) {
+  KrylovState next = st.clone();
+  bicgstabStep(aa, r0hat, next);
+  return next;
 }
 inline KrylovState cgsInit(const SpMatrix& aa, const SpVector& b, const SpVector& x0) {
   sla_krylov* st = nullptr;
@@ -276,6 +288,31 @@ inline SpVector linSolve0(LinSolveMethod method, const SpMatrix& aa, const SpVec
   SolveInfo* out = info ? info : &local;
   aa.ctx().check(sla_linsolve0(aa.ctx().get(), (int)method, aa.get(), b.get(), x0.get(), nullptr, x.get(), &out->iters, &out->resnorm));
   return x;
+}
+
+// restarted GMRES(m) — the algorithm behind (<\>) (Sparse.hs:837-848): Arnoldi with Givens rotations on the device, restart until the
+// true residual meets max tol_abs (tol_rel * ||r0||) or max_iters Arnoldi steps are spent
+inline SpVector gmres(const SpMatrix& aa, const SpVector& b, const SpVector& x0, int restart = 30, SolveInfo* info = nullptr,
+                      const sla_solve_opts* opts = nullptr) {
+  SpVector x(aa.ctx(), x0.dim());
+  SolveInfo local;
+  SolveInfo* out = info ? info : &local;
+  aa.ctx().check(sla_gmres(aa.ctx().get(), aa.get(), b.get(), x0.get(), restart, opts, x.get(), &out->iters, &out->resnorm));
+  return x;
+}
+inline SpVector backslash(const SpMatrix& aa, const SpVector& b) {          // aa <\> b, from x0 = 0
+  return gmres(aa, b, SpVector(aa.ctx(), b.dim()));
+}
+
+inline std::pair<SpMatrix, SpMatrix> ilu0Pre(const SpMatrix& aa) {           // (l, u): lu masked by the pattern of aa, Sparse.hs:696-706
+  sla_csr *l = nullptr, *u = nullptr;
+  aa.ctx().check(sla_ilu0_pre(aa.ctx().get(), aa.get(), &l, &u));
+  return {SpMatrix::adopt(aa.ctx(), l), SpMatrix::adopt(aa.ctx(), u)};
+}
+inline double normFrobenius(const SpMatrix& aa) {                            // sqrt (sum of squares), Class.hs:206-207
+  double d = 0;
+  aa.ctx().check(sla_csr_norm_frobenius(aa.ctx().get(), aa.get(), &d));
+  return d;
 }
 
 struct ArnoldiResult {
